@@ -1,0 +1,296 @@
+// Fused softmax(Q K^T * scale) V for the spatial self / cross attention of the adapter, the
+// ControlNet and the UNets.  tcgen05 MMAs with TMEM accumulators, TMA-fed 128B-swizzled
+// shared memory, online softmax in registers.
+//
+// One CTA = 128 query rows of one (batch, head) and one 64-wide slice of the value head dim.
+//   warp 0     : TMA producer (Q once, then K/V tiles of 128 keys through a 2-stage ring)
+//   warp 1     : MMA issuer + TMEM allocator.  S = Q K^T (M128 N128, K = 64*DQ) into TMEM cols [0,128);
+//                O_part = P V (M128 N64 K128, V consumed MN-major) into TMEM cols [128,192)
+//   warps 2..5 : softmax, one thread per query row: pass 1 row max, pass 2 exp2 / row sum / P -> bf16 ->
+//                swizzled smem (A operand of the PV MMA); O is accumulated in registers with the usual
+//                running-max rescale; final 1/l normalisation and 128 B row store.
+// With head dim 64 the CTA uses 112 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's
+// softmax overlaps the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ca {
+
+static constexpr int kAttnThreads = 192;
+static constexpr int kTileQ = 128;
+static constexpr int kTileKV = 128;
+static constexpr uint32_t kChunkBytes = 128 * 64 * 2;  // one [128 rows x 64 cols] bf16 swizzle tile = 16 KB
+
+template <int DQ>
+struct AttnCfg {
+  static constexpr int kStages = 2;
+  static constexpr uint32_t kQBytes = DQ * kChunkBytes;
+  static constexpr uint32_t kPBytes = 2 * kChunkBytes;
+  static constexpr uint32_t kStageBytes = (DQ + 1) * kChunkBytes;  // K chunks + one V slice
+  static constexpr uint32_t kSmemBytes = kQBytes + kPBytes + kStages * kStageBytes + 1024 + 128;
+  static constexpr uint32_t kTmemCols = 256;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DQ>
+__global__ void __launch_bounds__(kAttnThreads, (DQ == 1) ? 2 : 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<DQ>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_q = smem;
+  uint8_t* smem_p = smem + Cfg::kQBytes;
+  uint8_t* smem_kv = smem_p + Cfg::kPBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* o_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTileQ;
+  const int b = blockIdx.y / p.heads;
+  const int h = blockIdx.y % p.heads;
+  const int vs = blockIdx.z;
+  const int dpad = 64 * p.v_slices;  // padded head dim (elements) in the Q/K/V channel layout
+  const int nkv = (p.lk + kTileKV - 1) / kTileKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+      for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], Cfg::kStageBytes);
+        uint8_t* dst = smem_kv + st * Cfg::kStageBytes;
+        for (int c = 0; c < DQ; ++c)
+          tma_load_3d(dst + c * kChunkBytes, &tmap_k, &kv_full[st], h * dpad + c * 64, j * kTileKV, b);
+        tma_load_3d(dst + DQ * kChunkBytes, &tmap_v, &kv_full[st], h * dpad + vs * 64, j * kTileKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V tile) is MN-major
+      const uint32_t q_addr = smem_u32(smem_q);
+      const uint32_t p_addr = smem_u32(smem_p);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        mbar_wait(s_empty, (j & 1) ^ 1);  // softmax finished reading S of tile j-1
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(smem_kv + st * Cfg::kStageBytes);
+#pragma unroll
+        for (int c = 0; c < DQ; ++c) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(q_addr + c * kChunkBytes + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc_sw128(k_addr + c * kChunkBytes + k * 32, 16, 1024);
+            umma_bf16_ss(tmem_s, da, db, idesc_s, (c | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) issue_qk(j + 1);
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(o_empty, (j & 1) ^ 1);  // softmax consumed O_part of tile j-1
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * kChunkBytes + (k & 3) * 32, 16, 1024);
+          const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
+          umma_bf16_ss(tmem_o, da, db, idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    // ===================== softmax / output: one thread per query row =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o_acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    uint8_t* p_row = smem_p + r * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < nkv; ++j) {
+      const int kv_valid = min(kTileKV, p.lk - j * kTileKV);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // ---- pass 1: row max ----
+      float mx = m_run;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tmem_s + lane_sel + c * 32, sv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = (c * 32 + i < kv_valid) ? __uint_as_float(sv[i]) : -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = mx;
+      const float alpha = fast_exp2((m_run - m_new) * sl2);  // exp2(-inf) = 0 on the first tile
+      const float mneg = -m_new * sl2;
+      // P smem of tile j-1 must have been consumed by its PV MMA, whose result we also fold in now
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
+      // ---- pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P into the swizzled A tile ----
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tmem_s + lane_sel + c * 32, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), sl2, mneg));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), sl2, mneg));
+          if (c * 32 + i >= kv_valid) p0 = 0.f;
+          if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
+          rowsum += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        uint8_t* chunk = p_row + (c >> 1) * kChunkBytes;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 128-byte row
+          *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) =
+              make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      l_run = l_run * alpha + rowsum;
+      // ---- fold in O_part of tile j-1, then rescale to the new running max ----
+      if (j > 0) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(ov[i])) * alpha;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
+      }
+      fence_proxy_async_smem();  // P stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      m_run = m_new;
+    }
+    // last PV
+    mbar_wait(o_full, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int row = q0 + r;
+    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_batch_stride +
+                          static_cast<long long>(row) * p.out_row_stride + h * dpad + vs * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
+      tmem_ld_wait();
+      if (row < p.lq) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = (o_acc[c * 32 + u * 8 + e] + __uint_as_float(ov[u * 8 + e])) * inv_l;
+          *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = make_uint4(
+              pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int DQ>
+static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
+                             cudaStream_t stream) {
+  using Cfg = AttnCfg<DQ>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::kSmemBytes));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((p.lq + kTileQ - 1) / kTileQ, p.batch * p.heads, p.v_slices);
+  attention_kernel<DQ><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(q, k, v, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
+                             cudaStream_t stream) {
+  switch (p.dqk_chunks) {
+    case 1: return launch_dq<1>(q, k, v, p, stream);
+    case 2: return launch_dq<2>(q, k, v, p, stream);
+    case 3: return launch_dq<3>(q, k, v, p, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace ca

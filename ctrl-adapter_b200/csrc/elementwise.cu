@@ -1,0 +1,380 @@
+// Small HBM-bound kernels of the denoising step: timestep sinusoid, layout changes at the module boundary,
+// pooling / up-sampling, router softmax + weighted merge, CFG + scheduler update, temporal (frame-axis)
+// attention.  All vectorised to 16-byte accesses where the layout allows.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ca {
+
+static inline unsigned blocks_for(long long n, int threads, long long cap = 148LL * 32) {
+  long long b = (n + threads - 1) / threads;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<unsigned>(b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// diffusers Timesteps: emb = [sin(t f_k), cos(t f_k)], f_k = exp(-ln(1e4) k / (half - shift)); flip -> [cos, sin]
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, int flip, float shift,
+                                          int round_t, __nv_bfloat16* __restrict__ out) {
+  const int half = dim / 2;
+  const long long total = static_cast<long long>(n) * half;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int row = static_cast<int>(i / half), k = static_cast<int>(i % half);
+    float tv = t[row];
+    if (round_t) tv = round_bf16(tv);
+    const float exponent = -9.210340371976184f * static_cast<float>(k) / (static_cast<float>(half) - shift);
+    const float arg = tv * expf(exponent);
+    const float sv = sinf(arg), cv = cosf(arg);
+    __nv_bfloat16* o = out + static_cast<long long>(row) * dim;
+    if (flip) { o[k] = __float2bfloat16_rn(cv); o[half + k] = __float2bfloat16_rn(sv); }
+    else      { o[k] = __float2bfloat16_rn(sv); o[half + k] = __float2bfloat16_rn(cv); }
+    if ((dim & 1) && k == 0) o[dim - 1] = __float2bfloat16_rn(0.f);
+  }
+}
+cudaError_t launch_timestep_embedding(const float* t, int n, int dim, int flip_sin_to_cos, float freq_shift,
+                                      int round_t_bf16, __nv_bfloat16* out, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n) * (dim / 2);
+  timestep_embedding_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(t, n, dim, flip_sin_to_cos, freq_shift,
+                                                                        round_t_bf16, out);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// silu / add (bf16, 8 elements per thread; n must be a multiple of 8 -- all channel counts here are)
+// ---------------------------------------------------------------------------------------------
+__global__ void silu_kernel(const uint4* __restrict__ x, long long nvec, uint4* __restrict__ y) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 u = x[i];
+    const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float v = __bfloat162float(h[e]); f[e] = v / (1.0f + __expf(-v)); }
+    y[i] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+cudaError_t launch_silu(const __nv_bfloat16* x, long long n, __nv_bfloat16* y, cudaStream_t stream) {
+  if (n & 7) return cudaErrorInvalidValue;
+  silu_kernel<<<blocks_for(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), n / 8,
+                                                          reinterpret_cast<uint4*>(y));
+  return cudaGetLastError();
+}
+__global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, long long nvec,
+                           uint4* __restrict__ y) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 ua = a[i], ub = b[i];
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&ua);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&ub);
+    uint4 o;
+    uint32_t* po = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __bfloat1622float2(ha[e]), fb = __bfloat1622float2(hb[e]);
+      po[e] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+    }
+    y[i] = o;
+  }
+}
+cudaError_t launch_add(const __nv_bfloat16* a, const __nv_bfloat16* b, long long n, __nv_bfloat16* y,
+                       cudaStream_t stream) {
+  if (n & 7) return cudaErrorInvalidValue;
+  add_kernel<<<blocks_for(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(a),
+                                                         reinterpret_cast<const uint4*>(b), n / 8,
+                                                         reinterpret_cast<uint4*>(y));
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW <-> channels-last transposes through a 32x33 smem tile (coalesced on both sides)
+// ---------------------------------------------------------------------------------------------
+template <typename SrcT>
+__global__ void nchw_to_nhwc_kernel(const SrcT* __restrict__ x, int c, long long hw, int c_pad,
+                                    __nv_bfloat16* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ch = c0 + i;
+    const long long p = p0 + threadIdx.x;
+    float v = 0.f;
+    if (ch < c && p < hw) v = static_cast<float>(x[(static_cast<long long>(n) * c + ch) * hw + p]);
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i;
+    const int ch = c0 + threadIdx.x;
+    if (p < hw && ch < c_pad) y[(static_cast<long long>(n) * hw + p) * c_pad + ch] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+cudaError_t launch_nchw_to_nhwc(const void* x, int src_fp32, int n, int c, long long hw, int c_pad, __nv_bfloat16* y,
+                                cudaStream_t stream) {
+  dim3 grid(static_cast<unsigned>((hw + 31) / 32), (c_pad + 31) / 32, n), block(32, 8);
+  if (src_fp32) nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(x), c, hw, c_pad, y);
+  else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), c, hw, c_pad, y);
+  return cudaGetLastError();
+}
+template <typename DstT>
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int c, int c_stride, long long hw,
+                                    DstT* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i;
+    const int ch = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < hw && ch < c) v = __bfloat162float(x[(static_cast<long long>(n) * hw + p) * c_stride + ch]);
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ch = c0 + i;
+    const long long p = p0 + threadIdx.x;
+    if (ch < c && p < hw) y[(static_cast<long long>(n) * c + ch) * hw + p] = static_cast<DstT>(tile[threadIdx.x][i]);
+  }
+}
+cudaError_t launch_nhwc_to_nchw(const __nv_bfloat16* x, int n, int c, int c_stride, long long hw, void* y,
+                                int dst_fp32, cudaStream_t stream) {
+  dim3 grid(static_cast<unsigned>((hw + 31) / 32), (c + 31) / 32, n), block(32, 8);
+  if (dst_fp32) nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>(x, c, c_stride, hw, static_cast<float*>(y));
+  else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(x, c, c_stride, hw, static_cast<__nv_bfloat16*>(y));
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// adaptive average pool with integer ratio, channels-last (C small: latents / control image)
+// ---------------------------------------------------------------------------------------------
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, int h, int w, int c, int oh, int ow,
+                               long long total, __nv_bfloat16* __restrict__ y) {
+  const int ry = h / oh, rx = w / ow;
+  const float inv = 1.0f / static_cast<float>(ry * rx);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c);
+    long long t = i / c;
+    const int ox = static_cast<int>(t % ow); t /= ow;
+    const int oy = static_cast<int>(t % oh);
+    const long long n = t / oh;
+    float acc = 0.f;
+    for (int dy = 0; dy < ry; ++dy)
+      for (int dx = 0; dx < rx; ++dx)
+        acc += __bfloat162float(x[((n * h + oy * ry + dy) * w + ox * rx + dx) * c + ch]);
+    y[i] = __float2bfloat16_rn(acc * inv);
+  }
+}
+cudaError_t launch_avgpool(const __nv_bfloat16* x, int n, int h, int w, int c, int oh, int ow, __nv_bfloat16* y,
+                           cudaStream_t stream) {
+  if (h % oh != 0 || w % ow != 0) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(n) * oh * ow * c;
+  avgpool_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(x, h, w, c, oh, ow, total, y);
+  return cudaGetLastError();
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int h, int w, int nvec, long long total,
+                                  uint4* __restrict__ y) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    long long t = i / nvec;
+    const int px = static_cast<int>(t % w); t /= w;
+    const int py = static_cast<int>(t % h);
+    const long long n = t / h;
+    const uint4 u = x[i];
+    const long long ow = 2LL * w;
+    uint4* dst = y + ((n * 2 * h + 2 * py) * ow + 2 * px) * nvec + v;
+    dst[0] = u; dst[nvec] = u; dst[ow * nvec] = u; dst[ow * nvec + nvec] = u;
+  }
+}
+cudaError_t launch_upsample2x(const __nv_bfloat16* x, int n, int h, int w, int c, __nv_bfloat16* y,
+                              cudaStream_t stream) {
+  if (c & 7) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), h, w, c / 8, total,
+                                                                reinterpret_cast<uint4*>(y));
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Router: one warp per router; masked softmax over <= 32 experts by warp shuffles (ctrl_router.py:96-107)
+// ---------------------------------------------------------------------------------------------
+__global__ void router_weights_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ mask,
+                                      int nrouters, int nexperts, float* __restrict__ weights) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= nrouters) return;
+  const int lane = threadIdx.x & 31;
+  float v = -INFINITY;
+  if (lane < nexperts) {
+    v = logits[r * nexperts + lane];
+    if (mask != nullptr && mask[lane] == 0) v -= 1e6f;
+  }
+  float mx = v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float e = (lane < nexperts) ? expf(v - mx) : 0.f;
+  float s = e;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane < nexperts) weights[r * nexperts + lane] = e / s;
+}
+cudaError_t launch_router_weights(const float* logits, const unsigned char* mask, int nrouters, int nexperts,
+                                  float* weights, cudaStream_t stream) {
+  if (nexperts > 32 || nexperts < 1) return cudaErrorInvalidValue;
+  const int wpb = 4;
+  router_weights_kernel<<<(nrouters + wpb - 1) / wpb, wpb * 32, 0, stream>>>(logits, mask, nrouters, nexperts, weights);
+  return cudaGetLastError();
+}
+
+// y = sum_e w[e] * x_e with the reference's bf16 rounding after each multiply and add
+__global__ void router_merge_kernel(const __nv_bfloat16* const* __restrict__ xs, const float* __restrict__ w,
+                                    int nactive, long long nvec, uint4* __restrict__ y) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int k = 0; k < nactive; ++k) {
+      const float wk = round_bf16(w[k]);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xs[k]) + i);
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float prod = round_bf16(__bfloat162float(h[e]) * wk);
+        acc[e] = (k == 0) ? prod : round_bf16(acc[e] + prod);
+      }
+    }
+    y[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                      pack_bf16x2(acc[6], acc[7]));
+  }
+}
+cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, int nactive, long long n,
+                                __nv_bfloat16* y, cudaStream_t stream) {
+  if (n & 7) return cudaErrorInvalidValue;
+  router_merge_kernel<<<blocks_for(n / 8, 256), 256, 0, stream>>>(xs, w, nactive, n / 8, reinterpret_cast<uint4*>(y));
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// CFG + scheduler step.  Latents are carried in fp32 between steps (the schedulers up-cast internally);
+// the next step's model input (scaled, bf16) is produced in the same pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void cfg_euler_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
+                                 const float* __restrict__ lat, long long n, float g, float sigma, float sigma_next,
+                                 float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in, float next_scale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float u = __bfloat162float(eu[i]), c = __bfloat162float(et[i]);
+    const float eps = round_bf16(u + round_bf16(g * round_bf16(c - u)));
+    const float x = lat[i];
+    const float x0 = x - sigma * eps;
+    const float d = (x - x0) / sigma;
+    const float xn = x + d * (sigma_next - sigma);
+    lat_out[i] = xn;
+    if (next_in) next_in[i] = __float2bfloat16_rn(xn * next_scale);
+  }
+}
+cudaError_t launch_cfg_euler(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
+                             long long n, float guidance, float sigma, float sigma_next, int /*pred_type*/,
+                             float* latents_out, __nv_bfloat16* model_in_next, float next_in_scale,
+                             cudaStream_t stream) {
+  cfg_euler_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, sigma,
+                                                           sigma_next, latents_out, model_in_next, next_in_scale);
+  return cudaGetLastError();
+}
+__global__ void cfg_ddim_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
+                                const float* __restrict__ lat, long long n, float g, float a_t, float a_prev,
+                                float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
+  const float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), sap = sqrtf(a_prev), sbp = sqrtf(1.f - a_prev);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float u = __bfloat162float(eu[i]), c = __bfloat162float(et[i]);
+    const float eps = round_bf16(u + round_bf16(g * round_bf16(c - u)));
+    const float x = lat[i];
+    const float x0 = (x - sb * eps) / sa;
+    const float xn = sap * x0 + sbp * eps;
+    lat_out[i] = xn;
+    if (next_in) next_in[i] = __float2bfloat16_rn(xn);
+  }
+}
+cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
+                            long long n, float guidance, float alpha_t, float alpha_prev, float* latents_out,
+                            __nv_bfloat16* model_in_next, cudaStream_t stream) {
+  cfg_ddim_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, alpha_t,
+                                                          alpha_prev, latents_out, model_in_next);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Temporal self-attention: sequence = the F frames of one pixel, head dim 64.  HBM-bound (every Q/K/V element is
+// read once), so plain FMA: one warp per (clip, pixel, head); lane i owns head-dim elements {2i, 2i+1}.
+// Layout [clip][frame][pixel][heads*64]; frames <= 32.
+// ---------------------------------------------------------------------------------------------
+__global__ void temporal_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                          const __nv_bfloat16* __restrict__ v, int frames, long long hw, int heads,
+                                          float scale, long long total_warps, __nv_bfloat16* __restrict__ out) {
+  const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  if (wid >= total_warps) return;
+  const int lane = threadIdx.x & 31;
+  const int head = static_cast<int>(wid % heads);
+  long long t = wid / heads;
+  const long long pix = t % hw;
+  const long long clip = t / hw;
+  const long long cstride = static_cast<long long>(heads) * 64;
+  const long long fstride = hw * cstride;
+  const long long base = (clip * frames * hw + pix) * cstride + head * 64 + lane * 2;
+  float2 kf[32], vf[32];
+#pragma unroll
+  for (int f = 0; f < 32; ++f) {
+    if (f < frames) {
+      kf[f] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(k + base + f * fstride));
+      vf[f] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + base + f * fstride));
+    }
+  }
+  for (int i = 0; i < frames; ++i) {
+    const float2 qf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + base + i * fstride));
+    float s[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int f = 0; f < 32; ++f) {
+      if (f < frames) {
+        float d = qf.x * kf[f].x + qf.y * kf[f].y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        s[f] = d * scale;
+        mx = fmaxf(mx, s[f]);
+      }
+    }
+    float l = 0.f, ox = 0.f, oy = 0.f;
+#pragma unroll
+    for (int f = 0; f < 32; ++f) {
+      if (f < frames) {
+        const float p = __expf(s[f] - mx);
+        l += p;
+        const float pb = round_bf16(p);  // P is bf16 in the fused SDPA kernels of the reference path
+        ox += pb * vf[f].x;
+        oy += pb * vf[f].y;
+      }
+    }
+    const float inv = 1.0f / l;
+    *reinterpret_cast<__nv_bfloat162*>(out + base + i * fstride) = __floats2bfloat162_rn(ox * inv, oy * inv);
+  }
+}
+cudaError_t launch_temporal_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int clips,
+                                      int frames, long long hw, int heads, float scale, __nv_bfloat16* out,
+                                      cudaStream_t stream) {
+  if (frames > 32 || frames < 1) return cudaErrorInvalidValue;
+  const long long total_warps = static_cast<long long>(clips) * hw * heads;
+  const int threads = 128;
+  const long long blocks = (total_warps * 32 + threads - 1) / threads;
+  temporal_attention_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(q, k, v, frames, hw, heads, scale,
+                                                                                  total_warps, out);
+  return cudaGetLastError();
+}
+
+}  // namespace ca

@@ -1,0 +1,345 @@
+// Multi-tap tcgen05 GEMM: the one contraction kernel behind every Linear, 1x1 / 3x3
+// (stride 1 or 2) Conv2d and (3,1,1) temporal Conv3d on the denoising hot path.
+//
+//   out[row, n] = epilogue( sum_{tap} sum_{src} sum_{c} A_src[row + off(tap), c] * W[n, tap, src, c] )
+//
+// Activations live in HBM channels-last ([..., C] bf16).  "row" is a point of a
+// 4-D output row space (e.g. x, y, sample for a conv); a CTA tile covers a 4-D box
+// of 128 rows which TMA fetches as one 5-D box per (tap, 64-channel chunk) with
+// hardware zero fill outside the tensor -- i.e. implicit-GEMM convolution with no
+// im2col buffer.  Weights are [N][taps*K] bf16 (K contiguous).
+//
+// Structure (persistent, warp specialised, one CTA per SM):
+//   warp 0  : TMA producer  (A box + W tile per k-iteration into a 4-stage smem ring)
+//   warp 1  : MMA issuer    (single thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16)
+//   warp 2  : TMEM allocator
+//   warps 4-7: epilogue     (tcgen05.ld -> bias / temb / SiLU / GEGLU / scale / residual / blend -> bf16 store)
+// Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ca {
+
+static constexpr int kBM = 128;
+static constexpr int kBK = 64;
+static constexpr int kGemmThreads = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
+  static constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr uint32_t kBBytes = BN * kBK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kTmemCols = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);  // 2 accumulator stages
+  static constexpr uint32_t kAccStride = kTmemCols / 2;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
+                 const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint8_t* smem_a = smem;                                    // kStages x 16 KB
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;      // kStages x BN*128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                     // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;     // [kStages]
+  uint64_t* acc_full = bars + 2 * Cfg::kStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_m = p.ntile[0] * p.ntile[1] * p.ntile[2] * p.ntile[3];
+  const int total_tiles = tiles_m * p.n_tiles_n;
+  const int chunks0 = (p.src_c[0] + kBK - 1) / kBK;
+  const int chunks1 = (p.nsrc > 1) ? (p.src_c[1] + kBK - 1) / kBK : 0;
+  const int kiters = p.ntaps * (chunks0 + chunks1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a0);
+    if (p.nsrc > 1) tma_prefetch_desc(&tmap_a1);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tn = tile % p.n_tiles_n;
+        int tm = tile / p.n_tiles_n;
+        const int t1 = tm % p.ntile[0]; tm /= p.ntile[0];
+        const int t2 = tm % p.ntile[1]; tm /= p.ntile[1];
+        const int t3 = tm % p.ntile[2]; tm /= p.ntile[2];
+        const int t4 = tm;
+        const int o1 = t1 * p.box[0], o2 = t2 * p.box[1], o3 = t3 * p.box[2], o4 = t4 * p.box[3];
+        const int n0 = tn * BN;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int c1 = o1 + p.tap_off[tap][0], c2 = o2 + p.tap_off[tap][1];
+          const int c3 = o3 + p.tap_off[tap][2], c4 = o4 + p.tap_off[tap][3];
+          const int kbase = tap * p.k_per_tap;
+          for (int ch = 0; ch < chunks0 + chunks1; ++ch) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            const bool second = ch >= chunks0;
+            const int cc = (second ? (ch - chunks0) : ch) * kBK;
+            tma_load_5d(smem_a + stage * Cfg::kABytes, second ? &tmap_a1 : &tmap_a0, &full_bar[stage],
+                        cc + (second ? p.src_c0_off[1] : p.src_c0_off[0]) + p.tap_c_off[tap], c1, c2, c3, c4);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_w, &full_bar[stage],
+                        kbase + (second ? p.src_c[0] : 0) + cc, n0);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs above retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;       // row of the tile owned by this thread
+    const bool geglu = (p.act == CA_ACT_GEGLU);
+    const int ncols_out = geglu ? BN / 2 : BN;  // output columns produced per tile
+    float alpha_s = 0.f, alpha_t = 0.f;
+    if (p.blend_src != nullptr) {
+      const float a = *p.blend_alpha;  // bf16-valued
+      alpha_s = a;
+      alpha_t = round_bf16(1.0f - a);
+    }
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int tn = tile % p.n_tiles_n;
+      int tm = tile / p.n_tiles_n;
+      const int t1 = tm % p.ntile[0]; tm /= p.ntile[0];
+      const int t2 = tm % p.ntile[1]; tm /= p.ntile[1];
+      const int t3 = tm % p.ntile[2]; tm /= p.ntile[2];
+      const int t4 = tm;
+      int rr = r;
+      const int i1 = rr % p.box[0]; rr /= p.box[0];
+      const int i2 = rr % p.box[1]; rr /= p.box[1];
+      const int i3 = rr % p.box[2]; rr /= p.box[2];
+      const int i4 = rr;
+      const int o[4] = {t1 * p.box[0] + i1, t2 * p.box[1] + i2, t3 * p.box[2] + i3, t4 * p.box[3] + i4};
+      const bool row_ok = o[0] < p.odim[0] && o[1] < p.odim[1] && o[2] < p.odim[2] && o[3] < p.odim[3];
+      const long long out_off = o[0] * p.ostride[0] + o[1] * p.ostride[1] + o[2] * p.ostride[2] + o[3] * p.ostride[3];
+      const long long res_off = o[0] * p.rstride[0] + o[1] * p.rstride[1] + o[2] * p.rstride[2] + o[3] * p.rstride[3];
+      const long long rv_off = (p.rowvec != nullptr)
+                                   ? (o[0] * p.vstride[0] + o[1] * p.vstride[1] + o[2] * p.vstride[2] + o[3] * p.vstride[3])
+                                   : 0;
+      const int col_base = tn * ncols_out;  // first output column of this tile
+
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+
+      for (int c0 = 0; c0 < ncols_out; c0 += 32) {
+        if (col_base + c0 >= p.n_out) break;  // whole chunk beyond N (partial last N tile)
+        uint32_t va[32];
+        float v[32];
+        tmem_ld_32x32(t_row + c0, va);
+        if (geglu) {
+          uint32_t vg[32];
+          tmem_ld_32x32(t_row + BN / 2 + c0, vg);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int wa = tn * BN + c0 + j;           // weight row (a half)
+            const int wg = tn * BN + BN / 2 + c0 + j;  // weight row (gate half)
+            float a = __uint_as_float(va[j]);
+            float g = __uint_as_float(vg[j]);
+            if (p.bias != nullptr) { a += __ldg(p.bias + wa); g += __ldg(p.bias + wg); }
+            a = round_bf16(a);
+            g = round_bf16(g);
+            const float gl = round_bf16(0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)));
+            v[j] = round_bf16(a * gl);
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(va[j]);
+            if (p.bias != nullptr) x += __ldg(p.bias + min(col_base + c0 + j, p.n_out - 1));
+            v[j] = x;
+          }
+          if (!p.out_fp32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j]);
+          }
+          if (p.act == CA_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j] / (1.0f + __expf(-v[j])));
+          }
+        }
+        if (p.out_scale != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j] * p.out_scale);
+        }
+        if (row_ok) {
+          const int col = col_base + c0;
+          const int nvalid = min(32, p.n_out - col);
+          if (p.rowvec != nullptr) {
+            const __nv_bfloat16* rv = p.rowvec + rv_off + col;
+            if (nvalid == 32) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(rv) + j8);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  v[j8 * 8 + e * 2] = round_bf16(v[j8 * 8 + e * 2] + f.x);
+                  v[j8 * 8 + e * 2 + 1] = round_bf16(v[j8 * 8 + e * 2 + 1] + f.y);
+                }
+              }
+            } else {
+              for (int j = 0; j < nvalid; ++j) v[j] = round_bf16(v[j] + __bfloat162float(rv[j]));
+            }
+          }
+          if (p.residual != nullptr) {
+            const __nv_bfloat16* rs = p.residual + res_off + col;
+            if (nvalid == 32) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                const uint4 u = *(reinterpret_cast<const uint4*>(rs) + j8);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __bfloat1622float2(h[e]);
+                  v[j8 * 8 + e * 2] = round_bf16(v[j8 * 8 + e * 2] + f.x);
+                  v[j8 * 8 + e * 2 + 1] = round_bf16(v[j8 * 8 + e * 2 + 1] + f.y);
+                }
+              }
+            } else {
+              for (int j = 0; j < nvalid; ++j) v[j] = round_bf16(v[j] + __bfloat162float(rs[j]));
+            }
+          }
+          if (p.blend_src != nullptr) {
+            const __nv_bfloat16* bs = p.blend_src + res_off + col;
+            for (int j = 0; j < nvalid; ++j) {
+              const float xs = __bfloat162float(bs[j]);
+              v[j] = round_bf16(round_bf16(alpha_s * xs) + round_bf16(alpha_t * v[j]));
+            }
+          }
+          if (p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.out) + out_off + col;
+            if (nvalid == 32) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                reinterpret_cast<float4*>(op)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+            } else {
+              for (int j = 0; j < nvalid; ++j) op[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + col;
+            if (nvalid == 32) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint4 u;
+                u.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+                u.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                u.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+                u.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+                reinterpret_cast<uint4*>(op)[j8] = u;
+              }
+            } else {
+              for (int j = 0; j < nvalid; ++j) op[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN>
+static cudaError_t launch_bn(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmParams& p,
+                             int grid, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::kSmemBytes));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  gemm_conv_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a0, a1, w, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_conv(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+                             const GemmParams& p, int grid, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_bn<64>(a0, a1, w, p, grid, stream);
+    case 128: return launch_bn<128>(a0, a1, w, p, grid, stream);
+    case 160: return launch_bn<160>(a0, a1, w, p, grid, stream);
+    case 256: return launch_bn<256>(a0, a1, w, p, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace ca

@@ -1,0 +1,468 @@
+"""Torch-tensor front end of the C ABI: builds the descriptors (boxes, taps, strides) and launches on the
+current CUDA stream.  PyTorch is used only for device memory and streams; every computation below runs in
+the hand-written sm_100a kernels of ``csrc/`` (no fallback path).
+
+Layouts: activations are channels-last, ``[N, H, W, C]`` / ``[tokens, C]`` bf16 contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GEGLU, ACT_NONE, ACT_SILU, AttentionDesc, GemmDesc, check
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype=BF16):
+    if not t.is_cuda:
+        raise ValueError("ctrl_adapter_b200 ops need CUDA tensors (there is no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("expected a contiguous tensor")
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing (host side, once at load time)
+# ----------------------------------------------------------------------------------------------
+def pack_conv_weight(w: torch.Tensor, k_pad_to: int = 8) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] (or [Cout, Cin, kt, 1, 1]) -> [Cout, taps * Kp] with K = Cin zero padded to `k_pad_to`."""
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    wp = w.reshape(cout, cin, taps).permute(0, 2, 1)  # [Cout, taps, Cin]
+    kp = (cin + k_pad_to - 1) // k_pad_to * k_pad_to
+    if kp != cin:
+        wp = torch.nn.functional.pad(wp, (0, kp - cin))
+    return wp.reshape(cout, taps * kp).contiguous().to(BF16)
+
+
+def pack_geglu_weight(w: torch.Tensor, b: Optional[torch.Tensor], bn: int = 256):
+    """GEGLU proj [2*D, K] (value rows then gate rows) -> rows interleaved per n-tile of `bn`."""
+    d = w.shape[0] // 2
+    half = bn // 2
+    assert d % half == 0
+    wv, wg = w[:d].reshape(d // half, half, -1), w[d:].reshape(d // half, half, -1)
+    wi = torch.cat([wv, wg], dim=1).reshape(2 * d, -1).contiguous()
+    bi = None
+    if b is not None:
+        bv, bg = b[:d].reshape(d // half, half), b[d:].reshape(d // half, half)
+        bi = torch.cat([bv, bg], dim=1).reshape(2 * d).contiguous()
+    return wi, bi
+
+
+def bias_f32(b: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Biases are consumed as fp32 holding the bf16-rounded value (autocast casts them to bf16)."""
+    return None if b is None else b.to(BF16).float().contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# box heuristics: split the 128-row tile over (x, y, n) minimising padded work
+# ----------------------------------------------------------------------------------------------
+def choose_box(w: int, h: int, n: int):
+    best = None
+    for lw in range(8):
+        bw = 1 << lw
+        for lh in range(8 - lw):
+            bh = 1 << lh
+            bn_ = 128 // (bw * bh)
+            tiles = math.ceil(w / bw) * math.ceil(h / bh) * math.ceil(n / bn_)
+            key = (tiles, -bw, -bh)
+            if best is None or key < best[0]:
+                best = (key, (bw, bh, bn_))
+    return best[1]
+
+
+# ----------------------------------------------------------------------------------------------
+# GEMM family
+# ----------------------------------------------------------------------------------------------
+def _fill_epilogue(d: GemmDesc, *, bias, act, out_scale, rowvec, rowvec_strides, residual, blend_src, res_strides,
+                   blend_alpha):
+    d.bias = _ptr(bias)
+    d.act = act
+    d.out_scale = float(out_scale)
+    d.rowvec = _ptr(rowvec)
+    d.residual = _ptr(residual)
+    d.blend_src = _ptr(blend_src)
+    d.blend_alpha = _ptr(blend_alpha)
+    for i in range(4):
+        d.rowvec_strides[i] = rowvec_strides[i] if rowvec_strides else 0
+        d.res_strides[i] = res_strides[i] if res_strides else 0
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+           residual: Optional[torch.Tensor] = None, rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 0,
+           blend_src: Optional[torch.Tensor] = None, blend_alpha: Optional[torch.Tensor] = None,
+           out_scale: float = 1.0, out: Optional[torch.Tensor] = None, out_fp32: bool = False, bn: int = 0):
+    """y[M, N] = epilogue(x[M, K] @ w[N, K]^T).  `rowvec` [M / rows_per_vec, N] is broadcast over consecutive rows."""
+    _req(x); _req(w)
+    m, k = x.shape
+    wr = w.shape[0]
+    n_out = wr // 2 if act == ACT_GEGLU else wr
+    if out is None:
+        out = torch.empty((m, n_out), device=x.device, dtype=torch.float32 if out_fp32 else BF16)
+    d = GemmDesc()
+    d.nsrc = 1
+    d.a[0] = x.data_ptr()
+    d.a_channels[0] = k; d.a_c_off[0] = 0; d.a_c_len[0] = k
+    d.a_dims[0], d.a_dims[1], d.a_dims[2], d.a_dims[3] = m, 1, 1, 1
+    st = (k, m * k, m * k, m * k)
+    for i in range(4):
+        d.a_strides[0][i] = st[i]
+    d.box[0], d.box[1], d.box[2], d.box[3] = 128, 1, 1, 1
+    d.ntaps = 1
+    d.w = w.data_ptr(); d.w_rows = wr; d.w_k_per_tap = w.shape[1]
+    d.out = out.data_ptr(); d.out_fp32 = int(out_fp32); d.n_out = n_out
+    d.out_dims[0], d.out_dims[1], d.out_dims[2], d.out_dims[3] = m, 1, 1, 1
+    d.out_strides[0] = out.stride(0)
+    d.bn = bn
+    if rowvec is not None:
+        # rowvec index = row // rows_per_vec: expressed by splitting the row space as (rows_per_vec, M/rows_per_vec)
+        if rows_per_vec <= 0 or m % rows_per_vec != 0:
+            raise ValueError("rows_per_vec must divide M")
+    rs = (residual.stride(0), 0, 0, 0) if residual is not None else (blend_src.stride(0), 0, 0, 0) if blend_src is not None else None
+    if rowvec is not None:
+        # re-express rows as (r % rpv, r // rpv): tile box stays 128 x 1 when rpv is a multiple of 128, otherwise
+        # use a 2-D box so that tiles do not straddle rowvec boundaries
+        rpv = rows_per_vec
+        nv = m // rpv
+        if rpv >= 128:
+            b0 = 128
+            b1 = 1
+        else:
+            b0 = 1 << (rpv.bit_length() - 1)  # largest power of two <= rpv
+            b1 = 128 // b0
+        d.a_dims[0], d.a_dims[1] = rpv, nv
+        d.a_strides[0][0], d.a_strides[0][1] = k, rpv * k
+        d.box[0], d.box[1] = b0, b1
+        d.out_dims[0], d.out_dims[1] = rpv, nv
+        d.out_strides[0], d.out_strides[1] = out.stride(0), rpv * out.stride(0)
+        rvs = (0, rowvec.stride(0), 0, 0)
+        if rs is not None:
+            rs = (rs[0], rpv * rs[0], 0, 0)
+    else:
+        rvs = None
+    _fill_epilogue(d, bias=bias, act=act, out_scale=out_scale, rowvec=rowvec, rowvec_strides=rvs, residual=residual,
+                   blend_src=blend_src, res_strides=rs, blend_alpha=blend_alpha)
+    check(_lib.load().ca_gemm(C.byref(d), _stream()), "ca_gemm(linear)")
+    return out
+
+
+_TAPS_3X3 = [(dy, dx) for dy in range(3) for dx in range(3)]
+
+
+def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], *, ksize: int = 3, stride: int = 1,
+           x2: Optional[torch.Tensor] = None, act: int = ACT_NONE, out_scale: float = 1.0,
+           rowvec: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+           blend_src: Optional[torch.Tensor] = None, blend_alpha: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, out_fp32: bool = False, bn: int = 0, k_per_tap: Optional[int] = None):
+    """Channels-last conv: x [N,H,W,C] (+ optional x2 [N,H,W,C2] concatenated on C), w_packed [Cout, taps*Kp].
+    ksize 1 or 3 (padding (ksize-1)/2), stride 1 or 2 (3x3 only).  rowvec [N, Cout] is broadcast per sample
+    (time-embedding add); residual / blend_src are [N, Ho, Wo, Cout]."""
+    _req(x); _req(w_packed)
+    n, h, w_, c = x.shape
+    c2 = 0
+    if x2 is not None:
+        _req(x2)
+        c2 = x2.shape[3]
+        assert x2.shape[:3] == x.shape[:3]
+    cout = w_packed.shape[0]
+    ntaps = ksize * ksize
+    kpt = k_per_tap if k_per_tap is not None else w_packed.shape[1] // ntaps
+    ho, wo = (h, w_) if stride == 1 else (h // 2, w_ // 2)
+    if out is None:
+        out = torch.empty((n, ho, wo, cout), device=x.device, dtype=torch.float32 if out_fp32 else BF16)
+    d = GemmDesc()
+    d.nsrc = 2 if x2 is not None else 1
+    d.a[0] = x.data_ptr()
+    d.a_c_off[0] = 0; d.a_c_len[0] = c
+    if x2 is not None:
+        d.a[1] = x2.data_ptr(); d.a_c_off[1] = 0; d.a_c_len[1] = c2
+    bw, bh, bnn = choose_box(wo, ho, n)
+    if stride == 1:
+        d.a_channels[0] = c; d.a_channels[1] = c2
+        d.a_dims[0], d.a_dims[1], d.a_dims[2], d.a_dims[3] = w_, h, n, 1
+        for s_, cc in ((0, c), (1, c2)):
+            if s_ == 1 and x2 is None:
+                break
+            d.a_strides[s_][0], d.a_strides[s_][1], d.a_strides[s_][2], d.a_strides[s_][3] = cc, w_ * cc, h * w_ * cc, n * h * w_ * cc
+        d.box[0], d.box[1], d.box[2], d.box[3] = bw, bh, bnn, 1
+        d.ntaps = ntaps
+        if ksize == 3:
+            for t, (dy, dx) in enumerate(_TAPS_3X3):
+                d.tap_off[t][0], d.tap_off[t][1] = dx - 1, dy - 1
+        d.out_dims[0], d.out_dims[1], d.out_dims[2], d.out_dims[3] = wo, ho, n, 1
+        os_ = (cout, wo * cout, ho * wo * cout, 0)
+        rvs = (0, 0, cout, 0)
+    else:
+        assert ksize == 3 and x2 is None and h % 2 == 0 and w_ % 2 == 0
+        # parity view: channel axis [x parity][C], row dims (x/2, y parity, y/2, n)
+        d.a_channels[0] = 2 * c
+        d.a_dims[0], d.a_dims[1], d.a_dims[2], d.a_dims[3] = w_ // 2, 2, h // 2, n
+        d.a_strides[0][0], d.a_strides[0][1], d.a_strides[0][2], d.a_strides[0][3] = 2 * c, w_ * c, 2 * w_ * c, h * w_ * c
+        d.box[0], d.box[1], d.box[2], d.box[3] = bw, 1, bh, bnn
+        d.ntaps = 9
+        for t, (dy, dx) in enumerate(_TAPS_3X3):
+            # input row 2*oy + dy - 1: dy=0 -> (parity 1, oy-1); dy=1 -> (0, oy); dy=2 -> (1, oy)
+            py, oyo = ((1, -1), (0, 0), (1, 0))[dy]
+            px, oxo = ((1, -1), (0, 0), (1, 0))[dx]
+            d.tap_off[t][0], d.tap_off[t][1], d.tap_off[t][2], d.tap_off[t][3] = oxo, py, oyo, 0
+            d.tap_c_off[t] = px * c
+        d.out_dims[0], d.out_dims[1], d.out_dims[2], d.out_dims[3] = wo, 1, ho, n
+        os_ = (cout, 0, wo * cout, ho * wo * cout)
+        rvs = (0, 0, 0, cout)
+    for i in range(4):
+        d.out_strides[i] = os_[i]
+    d.w = w_packed.data_ptr(); d.w_rows = cout; d.w_k_per_tap = kpt
+    d.out = out.data_ptr(); d.out_fp32 = int(out_fp32); d.n_out = cout
+    d.bn = bn
+    _fill_epilogue(d, bias=bias, act=act, out_scale=out_scale, rowvec=rowvec, rowvec_strides=rvs if rowvec is not None else None,
+                   residual=residual, blend_src=blend_src,
+                   res_strides=os_ if (residual is not None or blend_src is not None) else None, blend_alpha=blend_alpha)
+    check(_lib.load().ca_gemm(C.byref(d), _stream()), "ca_gemm(conv2d)")
+    return out
+
+
+def temporal_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor], frames: int, *,
+                  rowvec: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                  blend_src: Optional[torch.Tensor] = None, blend_alpha: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None):
+    """Conv3d kernel (3,1,1), padding (1,0,0) over the frame axis of x [B*F, H, W, C] (frames contiguous per clip).
+    rowvec [B*F, Cout] is broadcast per frame."""
+    _req(x); _req(w_packed)
+    bf, h, w_, c = x.shape
+    b = bf // frames
+    hw = h * w_
+    cout = w_packed.shape[0]
+    if out is None:
+        out = torch.empty((bf, h, w_, cout), device=x.device, dtype=BF16)
+    d = GemmDesc()
+    d.nsrc = 1
+    d.a[0] = x.data_ptr(); d.a_channels[0] = c; d.a_c_off[0] = 0; d.a_c_len[0] = c
+    d.a_dims[0], d.a_dims[1], d.a_dims[2], d.a_dims[3] = hw, frames, b, 1
+    d.a_strides[0][0], d.a_strides[0][1], d.a_strides[0][2], d.a_strides[0][3] = c, hw * c, frames * hw * c, bf * hw * c
+    bp = min(128, 1 << (hw.bit_length() - 1)) if hw < 128 else 128
+    bfm = 128 // bp
+    d.box[0], d.box[1], d.box[2], d.box[3] = bp, bfm, 1, 1
+    d.ntaps = 3
+    for t in range(3):
+        d.tap_off[t][1] = t - 1
+    d.out_dims[0], d.out_dims[1], d.out_dims[2], d.out_dims[3] = hw, frames, b, 1
+    os_ = (cout, hw * cout, frames * hw * cout, 0)
+    for i in range(4):
+        d.out_strides[i] = os_[i]
+    d.w = w_packed.data_ptr(); d.w_rows = cout; d.w_k_per_tap = w_packed.shape[1] // 3
+    d.out = out.data_ptr(); d.n_out = cout
+    _fill_epilogue(d, bias=bias, act=ACT_NONE, out_scale=1.0, rowvec=rowvec,
+                   rowvec_strides=(0, cout, frames * cout, 0) if rowvec is not None else None, residual=residual,
+                   blend_src=blend_src, res_strides=os_ if (residual is not None or blend_src is not None) else None,
+                   blend_alpha=blend_alpha)
+    check(_lib.load().ca_gemm(C.byref(d), _stream()), "ca_gemm(temporal_conv)")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, head_dim_pad: int, scale: float,
+              out: Optional[torch.Tensor] = None):
+    """q [B, Lq, heads*Dp], k/v [B, Lk, heads*Dp] (last dim contiguous, row/batch strided views allowed)."""
+    b, lq, ctot = q.shape
+    lk = k.shape[1]
+    assert ctot == heads * head_dim_pad and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    if out is None:
+        out = torch.empty((b, lq, ctot), device=q.device, dtype=BF16)
+    d = AttentionDesc()
+    d.q, d.k, d.v, d.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    d.batch, d.heads, d.lq, d.lk = b, heads, lq, lk
+    d.head_dim_pad = head_dim_pad
+    d.scale = float(scale)
+    d.q_row_stride, d.q_batch_stride = q.stride(1), q.stride(0)
+    d.k_row_stride, d.k_batch_stride = k.stride(1), k.stride(0)
+    d.v_row_stride, d.v_batch_stride = v.stride(1), v.stride(0)
+    d.out_row_stride, d.out_batch_stride = out.stride(1), out.stride(0)
+    check(_lib.load().ca_attention(C.byref(d), _stream()), "ca_attention")
+    return out
+
+
+def temporal_attention(q, k, v, clips: int, frames: int, hw: int, heads: int, scale: float, out=None):
+    _req(q); _req(k); _req(v)
+    if out is None:
+        out = torch.empty_like(q)
+    check(_lib.load().ca_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), clips, frames, hw, heads,
+                                            float(scale), out.data_ptr(), _stream()), "ca_temporal_attention")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# norms
+# ----------------------------------------------------------------------------------------------
+_gn_scratch = {}
+
+
+def _gn_sums(device, n: int, groups: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    need = n * groups * 2
+    buf = _gn_scratch.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(max(need, 8192), device=device, dtype=torch.float64)
+        _gn_scratch[key] = buf
+    return buf
+
+
+def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, groups: int = 32,
+               silu: bool = False, up2x: bool = False, x2: Optional[torch.Tensor] = None, imgs_per_sample: int = 1,
+               out: Optional[torch.Tensor] = None):
+    """x [N, H, W, C] (+x2 concatenated on C).  imgs_per_sample > 1: statistics span that many consecutive images
+    (the 5-D GroupNorm of the temporal ResNet)."""
+    _req(x)
+    n, h, w_, c = x.shape
+    c2 = x2.shape[3] if x2 is not None else 0
+    ct = c + c2
+    lib = _lib.load()
+    nsamp = n // imgs_per_sample
+    sums = torch.empty(nsamp * groups * 2, device=x.device, dtype=torch.float64)
+    check(lib.ca_groupnorm_stats(x.data_ptr(), c, _ptr(x2), c2, nsamp, imgs_per_sample * h * w_, groups,
+                                 sums.data_ptr(), _stream()), "ca_groupnorm_stats")
+    if out is None:
+        out = torch.empty((n, h * 2, w_ * 2, ct) if up2x else (n, h, w_, ct), device=x.device, dtype=BF16)
+    check(lib.ca_groupnorm_apply(x.data_ptr(), c, _ptr(x2), c2, n, h, w_, imgs_per_sample, groups, float(eps),
+                                 sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(silu), int(up2x),
+                                 out.data_ptr(), _stream()), "ca_groupnorm_apply")
+    return out
+
+
+def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *,
+               add_rowvec: Optional[torch.Tensor] = None, rows_per_vec: int = 0, return_sum: bool = False):
+    _req(x)
+    c = x.shape[-1]
+    rows = x.numel() // c
+    y = torch.empty_like(x)
+    ysum = torch.empty_like(x) if (add_rowvec is not None and return_sum) else None
+    check(_lib.load().ca_layernorm(x.data_ptr(), rows, c, float(eps), gamma.data_ptr(), beta.data_ptr(),
+                                   _ptr(add_rowvec), rows_per_vec, _ptr(ysum), y.data_ptr(), _stream()),
+          "ca_layernorm")
+    return (y, ysum) if return_sum else y
+
+
+# ----------------------------------------------------------------------------------------------
+# small kernels
+# ----------------------------------------------------------------------------------------------
+def timestep_embedding(t: torch.Tensor, dim: int, *, flip_sin_to_cos: bool = True, freq_shift: float = 0.0,
+                       round_t_bf16: bool = False):
+    _req(t, torch.float32)
+    n = t.numel()
+    out = torch.empty((n, dim), device=t.device, dtype=BF16)
+    check(_lib.load().ca_timestep_embedding(t.data_ptr(), n, dim, int(flip_sin_to_cos), float(freq_shift),
+                                            int(round_t_bf16), out.data_ptr(), _stream()), "ca_timestep_embedding")
+    return out
+
+
+def silu(x: torch.Tensor):
+    _req(x)
+    y = torch.empty_like(x)
+    check(_lib.load().ca_silu(x.data_ptr(), x.numel(), y.data_ptr(), _stream()), "ca_silu")
+    return y
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _req(a); _req(b)
+    y = torch.empty_like(a) if out is None else out
+    check(_lib.load().ca_add(a.data_ptr(), b.data_ptr(), a.numel(), y.data_ptr(), _stream()), "ca_add")
+    return y
+
+
+def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None):
+    """[N, C, H, W] bf16/fp32 contiguous -> [N, H, W, c_pad] bf16 (extra channels zero)."""
+    if not x.is_contiguous():
+        raise ValueError("expected contiguous NCHW")
+    n, c, h, w_ = x.shape
+    cp = c if c_pad is None else c_pad
+    y = torch.empty((n, h, w_, cp), device=x.device, dtype=BF16)
+    if x.dtype not in (BF16, torch.float32):
+        raise ValueError("nchw_to_nhwc: bf16 or fp32 input")
+    check(_lib.load().ca_nchw_to_nhwc(x.data_ptr(), int(x.dtype == torch.float32), n, c, h * w_, cp, y.data_ptr(),
+                                      _stream()), "ca_nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None, fp32: bool = False):
+    _req(x)
+    n, h, w_, cs = x.shape
+    cc = cs if c is None else c
+    y = torch.empty((n, cc, h, w_), device=x.device, dtype=torch.float32 if fp32 else BF16)
+    check(_lib.load().ca_nhwc_to_nchw(x.data_ptr(), n, cc, cs, h * w_, y.data_ptr(), int(fp32), _stream()),
+          "ca_nhwc_to_nchw")
+    return y
+
+
+def avgpool(x: torch.Tensor, oh: int, ow: int):
+    _req(x)
+    n, h, w_, c = x.shape
+    y = torch.empty((n, oh, ow, c), device=x.device, dtype=BF16)
+    check(_lib.load().ca_avgpool(x.data_ptr(), n, h, w_, c, oh, ow, y.data_ptr(), _stream()), "ca_avgpool")
+    return y
+
+
+def upsample2x(x: torch.Tensor):
+    _req(x)
+    n, h, w_, c = x.shape
+    y = torch.empty((n, 2 * h, 2 * w_, c), device=x.device, dtype=BF16)
+    check(_lib.load().ca_upsample2x(x.data_ptr(), n, h, w_, c, y.data_ptr(), _stream()), "ca_upsample2x")
+    return y
+
+
+def router_weights(logits: torch.Tensor, mask: Optional[torch.Tensor]):
+    """logits [R, E] fp32, mask [E] uint8 (0 = masked) -> softmax weights [R, E] fp32."""
+    _req(logits, torch.float32)
+    r, e = logits.shape
+    out = torch.empty_like(logits)
+    check(_lib.load().ca_router_weights(logits.data_ptr(), _ptr(mask), r, e, out.data_ptr(), _stream()),
+          "ca_router_weights")
+    return out
+
+
+def router_merge(xs: Sequence[torch.Tensor], w: torch.Tensor, ptr_table: Optional[torch.Tensor] = None):
+    """y = sum_k w[k] * xs[k] (bf16 rounding after every multiply / add as in the reference loop)."""
+    for x in xs:
+        _req(x)
+    _req(w, torch.float32)
+    if ptr_table is None:
+        ptr_table = torch.tensor([x.data_ptr() for x in xs], dtype=torch.int64).to(xs[0].device)
+    y = torch.empty_like(xs[0])
+    check(_lib.load().ca_router_merge(ptr_table.data_ptr(), w.data_ptr(), len(xs), xs[0].numel(), y.data_ptr(),
+                                      _stream()), "ca_router_merge")
+    return y
+
+
+def cfg_euler(eps_uncond, eps_text, latents, guidance, sigma, sigma_next, next_in_scale, latents_out=None,
+              model_in_next=None):
+    _req(eps_uncond); _req(eps_text); _req(latents, torch.float32)
+    if latents_out is None:
+        latents_out = torch.empty_like(latents)
+    check(_lib.load().ca_cfg_euler(eps_uncond.data_ptr(), eps_text.data_ptr(), latents.data_ptr(), latents.numel(),
+                                   float(guidance), float(sigma), float(sigma_next), latents_out.data_ptr(),
+                                   _ptr(model_in_next), float(next_in_scale), _stream()), "ca_cfg_euler")
+    return latents_out
+
+
+def cfg_ddim(eps_uncond, eps_text, latents, guidance, alpha_t, alpha_prev, latents_out=None, model_in_next=None):
+    _req(eps_uncond); _req(eps_text); _req(latents, torch.float32)
+    if latents_out is None:
+        latents_out = torch.empty_like(latents)
+    check(_lib.load().ca_cfg_ddim(eps_uncond.data_ptr(), eps_text.data_ptr(), latents.data_ptr(), latents.numel(),
+                                  float(guidance), float(alpha_t), float(alpha_prev), latents_out.data_ptr(),
+                                  _ptr(model_in_next), _stream()), "ca_cfg_ddim")
+    return latents_out
