@@ -1,0 +1,74 @@
+"""ORACLE (test infrastructure): the parity cases shared by the golden-vector generator (real reference classes
+through the diffusers shim), the oracle self-check and the GPU parity tests.  Every input is produced by
+oracle.weights.seeded_tensor so the three parties see identical values."""
+from __future__ import annotations
+
+import torch
+
+from .weights import seeded_tensor
+
+# residual shapes of the SD1.5 ControlNet for a base (latent) resolution r: 12 down tensors + mid
+CN_CHANNELS = [320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280]
+CN_DIV = [1, 1, 1, 2, 2, 2, 4, 4, 4, 8, 8, 8]
+
+
+def controlnet_residuals(n: int, r: int, seed: int = 0):
+    down = [seeded_tensor(f"down{i}", (n, c, max(r // d, 1), max(r // d, 1)), seed) for i, (c, d) in
+            enumerate(zip(CN_CHANNELS, CN_DIV))]
+    mid = seeded_tensor("mid", (n, 1280, max(r // 8, 1), max(r // 8, 1)), seed)
+    return down, mid
+
+
+ADAPTER_SDXL_KW = dict(backbone_model_name="sdxl", num_blocks=1, num_frames=1, num_adapters_per_location=3,
+                       cross_attention_dim=2048, add_spatial_resnet=True, add_temporal_resnet=False,
+                       add_spatial_transformer=True, add_temporal_transformer=False, add_adapter_location_A=True,
+                       add_adapter_location_B=True, add_adapter_location_C=True)  # configs/sdxl_train_depth.yaml:40-54
+
+ADAPTER_VIDEO_KW = dict(backbone_model_name="i2vgenxl", num_blocks=1, num_frames=4, num_adapters_per_location=3,
+                        cross_attention_dim=1024, add_spatial_resnet=True, add_temporal_resnet=True,
+                        add_spatial_transformer=True, add_temporal_transformer=True, add_adapter_location_A=True,
+                        add_adapter_location_B=True, add_adapter_location_C=True, add_adapter_location_D=True,
+                        add_adapter_location_M=True)  # configs/i2vgenxl_train_depth.yaml
+
+
+def adapter_sdxl_inputs(n: int = 2, r: int = 8, seed: int = 0):
+    down, _ = controlnet_residuals(n, r, seed)
+    ctx = seeded_tensor("prompt_embeds", (n, 77, 2048), seed)
+    return dict(down_block_res_samples=down, mid_block_res_sample=None, num_frames=1, timestep=torch.tensor(981.0),
+                encoder_hidden_states=ctx)
+
+
+def adapter_video_inputs(b: int = 1, f: int = 4, r: int = 8, seed: int = 0):
+    down, mid = controlnet_residuals(b * f, r, seed)
+    ctx = seeded_tensor("image_embeddings", (1, 1, 1024), seed)
+    return dict(down_block_res_samples=down, mid_block_res_sample=mid, num_frames=f, timestep=torch.tensor(501.0),
+                encoder_hidden_states=ctx)
+
+
+CONTROLNET_KW = dict(cross_attention_dim=768)  # lllyasviel/control_v11*_sd15_* (SD1.5) configuration
+
+
+def controlnet_inputs(n: int = 2, r: int = 8, seed: int = 0):
+    return dict(sample=seeded_tensor("cn_sample", (n, 4, r, r), seed), timestep=torch.tensor(961.0),
+                encoder_hidden_states=seeded_tensor("cn_ehs", (n, 77, 768), seed),
+                controlnet_cond=torch.sigmoid(seeded_tensor("cn_cond", (n, 3, 8 * r, 8 * r), seed)),
+                conditioning_scale=1.0, return_dict=False)
+
+
+ROUTER_KW = dict(num_experts=7, backbone_model_name="i2vgenxl", router_type="simple_weights", num_routers=12,
+                 add_mid_block_router=True)
+ROUTER_MASK = [1, 1, 0, 1, 0, 0, 0]  # inference.py:343-345 for control types [depth, canny, softedge]
+
+
+def unet_sdxl_inputs(n: int = 2, r: int = 16, seed: int = 0, with_residuals: bool = True):
+    """r = UNet latent resolution; adapter residuals follow the 9 SDXL skip shapes."""
+    chans = [320, 320, 320, 320, 640, 640, 640, 1280, 1280]
+    divs = [1, 1, 1, 2, 2, 2, 4, 4, 4]
+    res = [seeded_tensor(f"unet_res{i}", (n, c, r // d, r // d), seed, 0.5) for i, (c, d) in enumerate(zip(chans, divs))]
+    res += [torch.zeros(n, 1280, r // 4, r // 4)] * 3  # the adapter returns 12 tensors; zip() drops the last 3
+    return dict(sample=seeded_tensor("unet_sample", (n, 4, r, r), seed), timestep=torch.tensor(961.0),
+                encoder_hidden_states=seeded_tensor("unet_ehs", (n, 77, 2048), seed),
+                added_cond_kwargs=dict(text_embeds=seeded_tensor("unet_text_embeds", (n, 1280), seed),
+                                       time_ids=torch.tensor([[8.0 * r, 8.0 * r, 0, 0, 8.0 * r, 8.0 * r]] * n)),
+                down_block_additional_residuals=res if with_residuals else None,
+                mid_block_additional_residual=0 if with_residuals else None)
