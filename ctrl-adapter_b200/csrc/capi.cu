@@ -296,9 +296,10 @@ int ca_cfg_ddim(const void* eu, const void* et, const float* lat, int64_t n, flo
                                 (__nv_bfloat16*)next_in, (cudaStream_t)s), "cfg_ddim");
 }
 int ca_temporal_attention(const void* q, const void* k, const void* v, int32_t clips, int32_t frames, int64_t hw,
-                          int32_t heads, float scale, void* out, void* s) {
+                          int32_t heads, float scale, int64_t in_row_stride, void* out, void* s) {
   CA_LAUNCH(ca::launch_temporal_attention((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                          clips, frames, hw, heads, scale, (__nv_bfloat16*)out, (cudaStream_t)s),
+                                          clips, frames, hw, heads, scale, in_row_stride, (__nv_bfloat16*)out,
+                                          (cudaStream_t)s),
             "temporal_attention");
 }
 

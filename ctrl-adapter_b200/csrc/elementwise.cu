@@ -317,7 +317,8 @@ cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16
 // ---------------------------------------------------------------------------------------------
 __global__ void temporal_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                                           const __nv_bfloat16* __restrict__ v, int frames, long long hw, int heads,
-                                          float scale, long long total_warps, __nv_bfloat16* __restrict__ out) {
+                                          float scale, long long in_stride, long long total_warps,
+                                          __nv_bfloat16* __restrict__ out) {
   const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   if (wid >= total_warps) return;
   const int lane = threadIdx.x & 31;
@@ -326,8 +327,10 @@ __global__ void temporal_attention_kernel(const __nv_bfloat16* __restrict__ q, c
   const long long pix = t % hw;
   const long long clip = t / hw;
   const long long cstride = static_cast<long long>(heads) * 64;
-  const long long fstride = hw * cstride;
-  const long long base = (clip * frames * hw + pix) * cstride + head * 64 + lane * 2;
+  const long long fstride = hw * in_stride;   // input frame stride (rows may be views of a fused QKV buffer)
+  const long long ofstride = hw * cstride;    // output is dense
+  const long long base = (clip * frames * hw + pix) * in_stride + head * 64 + lane * 2;
+  const long long obase = (clip * frames * hw + pix) * cstride + head * 64 + lane * 2;
   float2 kf[32], vf[32];
 #pragma unroll
   for (int f = 0; f < 32; ++f) {
@@ -362,18 +365,18 @@ __global__ void temporal_attention_kernel(const __nv_bfloat16* __restrict__ q, c
       }
     }
     const float inv = 1.0f / l;
-    *reinterpret_cast<__nv_bfloat162*>(out + base + i * fstride) = __floats2bfloat162_rn(ox * inv, oy * inv);
+    *reinterpret_cast<__nv_bfloat162*>(out + obase + i * ofstride) = __floats2bfloat162_rn(ox * inv, oy * inv);
   }
 }
 cudaError_t launch_temporal_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int clips,
-                                      int frames, long long hw, int heads, float scale, __nv_bfloat16* out,
-                                      cudaStream_t stream) {
+                                      int frames, long long hw, int heads, float scale, long long in_row_stride,
+                                      __nv_bfloat16* out, cudaStream_t stream) {
   if (frames > 32 || frames < 1) return cudaErrorInvalidValue;
   const long long total_warps = static_cast<long long>(clips) * hw * heads;
   const int threads = 128;
   const long long blocks = (total_warps * 32 + threads - 1) / threads;
   temporal_attention_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(q, k, v, frames, hw, heads, scale,
-                                                                                  total_warps, out);
+                                                                                  in_row_stride, total_warps, out);
   return cudaGetLastError();
 }
 

@@ -87,6 +87,6 @@ cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16
                             __nv_bfloat16* model_in_next, cudaStream_t stream);
 cudaError_t launch_temporal_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
                                       int clips, int frames, long long hw, int heads, float scale,
-                                      __nv_bfloat16* out, cudaStream_t stream);
+                                      long long in_row_stride, __nv_bfloat16* out, cudaStream_t stream);
 
 }  // namespace ca

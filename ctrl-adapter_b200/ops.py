@@ -205,7 +205,7 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
                 d.tap_off[t][0], d.tap_off[t][1] = dx - 1, dy - 1
         d.out_dims[0], d.out_dims[1], d.out_dims[2], d.out_dims[3] = wo, ho, n, 1
         os_ = (cout, wo * cout, ho * wo * cout, 0)
-        rvs = (0, 0, cout, 0)
+        rvs = (0, 0, cout if (rowvec is not None and rowvec.shape[0] > 1) else 0, 0)
     else:
         assert ksize == 3 and x2 is None and h % 2 == 0 and w_ % 2 == 0
         # parity view: channel axis [x parity][C], row dims (x/2, y parity, y/2, n)
@@ -222,7 +222,7 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
             d.tap_c_off[t] = px * c
         d.out_dims[0], d.out_dims[1], d.out_dims[2], d.out_dims[3] = wo, 1, ho, n
         os_ = (cout, 0, wo * cout, ho * wo * cout)
-        rvs = (0, 0, 0, cout)
+        rvs = (0, 0, 0, cout if (rowvec is not None and rowvec.shape[0] > 1) else 0)
     for i in range(4):
         d.out_strides[i] = os_[i]
     d.w = w_packed.data_ptr(); d.w_rows = cout; d.w_k_per_tap = kpt
@@ -266,7 +266,8 @@ def temporal_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.
     d.w = w_packed.data_ptr(); d.w_rows = cout; d.w_k_per_tap = w_packed.shape[1] // 3
     d.out = out.data_ptr(); d.n_out = cout
     _fill_epilogue(d, bias=bias, act=ACT_NONE, out_scale=1.0, rowvec=rowvec,
-                   rowvec_strides=(0, cout, frames * cout, 0) if rowvec is not None else None, residual=residual,
+                   rowvec_strides=((0, cout, frames * cout, 0) if rowvec.shape[0] > 1 else (0, 0, 0, 0)) if rowvec is not None else None,
+                   residual=residual,
                    blend_src=blend_src, res_strides=os_ if (residual is not None or blend_src is not None) else None,
                    blend_alpha=blend_alpha)
     check(_lib.load().ca_gemm(C.byref(d), _stream()), "ca_gemm(temporal_conv)")
@@ -297,12 +298,15 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hea
     return out
 
 
-def temporal_attention(q, k, v, clips: int, frames: int, hw: int, heads: int, scale: float, out=None):
-    _req(q); _req(k); _req(v)
+def temporal_attention(q, k, v, clips: int, frames: int, hw: int, heads: int, scale: float, out=None,
+                       row_stride: Optional[int] = None):
+    """q/k/v: [clips*frames*hw, heads*64] rows (row stride `row_stride` elements, e.g. views of a fused QKV buffer)."""
+    c = heads * 64
+    rs = c if row_stride is None else row_stride
     if out is None:
-        out = torch.empty_like(q)
+        out = torch.empty((clips * frames * hw, c), device=q.device, dtype=BF16)
     check(_lib.load().ca_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), clips, frames, hw, heads,
-                                            float(scale), out.data_ptr(), _stream()), "ca_temporal_attention")
+                                            float(scale), rs, out.data_ptr(), _stream()), "ca_temporal_attention")
     return out
 
 

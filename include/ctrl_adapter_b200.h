@@ -180,11 +180,12 @@ int ca_cfg_ddim(const void* eps_uncond, const void* eps_text, const float* laten
 
 /*
  * Temporal self-attention over the frame axis (diffusers TemporalBasicTransformerBlock.attn1 reached from
- * model/adapter_spatial_temporal.py:280).  q/k/v/out: [clips*frames, hw, heads*64] bf16 in (clip, frame, pixel)
+ * model/adapter_spatial_temporal.py:280).  q/k/v: rows of heads*64 bf16 with stride in_row_stride elements (views of a
+ * fused QKV buffer), out: [clips*frames*hw, heads*64] dense; rows in (clip, frame, pixel)
  * order -- the (b f) s c <-> (b s) f c permutes of the reference are folded into the addressing.
  */
 int ca_temporal_attention(const void* q, const void* k, const void* v, int32_t clips, int32_t frames, int64_t hw,
-                          int32_t heads, float scale, void* out, void* cuda_stream);
+                          int32_t heads, float scale, int64_t in_row_stride, void* out, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -33,12 +33,14 @@ def _rand(*shape, scale=1.0, seed=None, dtype=BF16):
     return (torch.randn(*shape, generator=g, device="cuda", dtype=torch.float32) * scale).to(dtype)
 
 
-def _report(name, out, ref, rtol, atol, extra=None):
+def _report(name, out, ref, rtol, atol, extra=None, mag=None):
+    """mag: magnitude of the largest intermediate of a multi-step bf16 epilogue (a 1-ulp flip of an intermediate is
+    1 ulp of THAT magnitude, which can be several ulps of a smaller final value after cancellation)."""
     out = out.float()
     ref = ref.float()
     assert out.shape == ref.shape, f"{name}: shape {tuple(out.shape)} vs {tuple(ref.shape)}"
     err = (out - ref).abs()
-    tol = atol + rtol * ref.abs()
+    tol = atol + rtol * (ref.abs() if mag is None else torch.maximum(ref.abs(), mag.float().abs()))
     bad = (err > tol) | ~torch.isfinite(out)
     rec = {
         "check": name,
@@ -73,14 +75,16 @@ def check_linear(m, k, n, *, bn=0, bias=True, out_fp32=True, residual=False, act
         ref = ref.to(BF16).float()
     if act == "silu":
         ref = F.silu(ref).to(BF16).float()
+    mag = ref.abs().clone()
     if residual:
         ref = (ref + res.float()).to(BF16).float()
+        mag = torch.maximum(mag, res.float().abs())
     out = ops.linear(x, w, ops.bias_f32(b), act=ops.ACT_SILU if act == "silu" else ops.ACT_NONE, residual=res,
                      out_fp32=out_fp32, bn=bn)
     torch.cuda.synchronize()
     rtol, atol = (1e-3, 1e-4) if out_fp32 else (2 ** -7, 1e-3)
     return _report(f"linear m{m} k{k} n{n} bn{bn} {'f32' if out_fp32 else 'bf16'} act={act} res={int(residual)}",
-                   out, ref, rtol, atol)
+                   out, ref, rtol, atol, mag=mag)
 
 
 def check_geglu(m, k, d, seed=0):
@@ -102,11 +106,11 @@ def check_linear_rowvec(m, k, n, rpv, seed=0):
     x = _rand(m, k, seed=seed + 1)
     w = _rand(n, k, scale=1.0 / math.sqrt(k), seed=seed + 2)
     rv = _rand(m // rpv, n, seed=seed + 3)
-    ref = (x.float() @ w.float().t()).to(BF16).float()
-    ref = (ref + rv.float().repeat_interleave(rpv, dim=0)).to(BF16).float()
+    lin = (x.float() @ w.float().t()).to(BF16).float()
+    ref = (lin + rv.float().repeat_interleave(rpv, dim=0)).to(BF16).float()
     out = ops.linear(x, w, None, rowvec=rv, rows_per_vec=rpv)
     torch.cuda.synchronize()
-    return _report(f"linear+rowvec m{m} k{k} n{n} rpv{rpv}", out, ref, 2 ** -7, 1e-3)
+    return _report(f"linear+rowvec m{m} k{k} n{n} rpv{rpv}", out, ref, 2 ** -7, 1e-3, mag=lin)
 
 
 def check_linear_blend(m, k, n, seed=0):
@@ -120,7 +124,8 @@ def check_linear_blend(m, k, n, seed=0):
     ref = ((alpha * xs).to(BF16) + ((1.0 - alpha).to(BF16) * xt).to(BF16)).float()
     out = ops.linear(x, w, None, residual=res, blend_src=xs, blend_alpha=alpha.float())
     torch.cuda.synchronize()
-    return _report(f"linear+res+blend m{m} k{k} n{n}", out, ref, 2 ** -7, 1e-3)
+    mag = torch.maximum(torch.maximum(xt.float().abs(), res.float().abs()), xs.float().abs())
+    return _report(f"linear+res+blend m{m} k{k} n{n}", out, ref, 2 ** -7, 1e-3, mag=mag)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -145,12 +150,15 @@ def check_conv(n, h, w, cin, cout, *, ksize=3, stride=1, cin2=0, out_fp32=True, 
     if scale != 1.0:
         ref = (ref * scale).to(BF16).float()
     rv = res = None
+    mag = ref.abs().clone()
     if rowvec:
         rv = _rand(n, cout, seed=seed + 6)
         ref = (ref + rv.float()[:, :, None, None]).to(BF16).float()
+        mag = torch.maximum(mag, ref.abs())
     if residual:
         res = _rand(n, cout, ref.shape[2], ref.shape[3], seed=seed + 7)
         ref = (ref + res.float()).to(BF16).float()
+        mag = torch.maximum(mag, res.float().abs())
     kpad = 64 if stride == 2 else 8
     wp = ops.pack_conv_weight(wt, kpad)
     out = ops.conv2d(_nhwc(x), wp, ops.bias_f32(b), ksize=ksize, stride=stride, x2=_nhwc(x2) if x2 is not None else None,
@@ -158,7 +166,7 @@ def check_conv(n, h, w, cin, cout, *, ksize=3, stride=1, cin2=0, out_fp32=True, 
     torch.cuda.synchronize()
     rtol, atol = (1e-3, 1e-4) if out_fp32 else (2 ** -7, 1e-3)
     return _report(f"conv{ksize}x{ksize} s{stride} n{n} {h}x{w} c{cin}+{cin2}->{cout} {'f32' if out_fp32 else 'bf16'}"
-                   f" rv={int(rowvec)} res={int(residual)} sc={scale}", out.permute(0, 3, 1, 2), ref, rtol, atol)
+                   f" rv={int(rowvec)} res={int(residual)} sc={scale}", out.permute(0, 3, 1, 2), ref, rtol, atol, mag=mag)
 
 
 def check_temporal_conv(b, f, h, w, c, cout, seed=0):
@@ -168,12 +176,13 @@ def check_temporal_conv(b, f, h, w, c, cout, seed=0):
     bias = _rand(cout, seed=seed + 3)
     rv = _rand(b * f, cout, seed=seed + 4)
     ref = F.conv3d(x.float(), wt.float(), bias.float(), padding=(1, 0, 0)).to(BF16).float()
+    mag = ref.abs().clone()
     ref = (ref + rv.float().reshape(b, f, cout).permute(0, 2, 1)[:, :, :, None, None]).to(BF16).float()
     xl = x.permute(0, 2, 3, 4, 1).reshape(b * f, h, w, c).contiguous()
     out = ops.temporal_conv(xl, ops.pack_conv_weight(wt), ops.bias_f32(bias), f, rowvec=rv)
     torch.cuda.synchronize()
     out5 = out.reshape(b, f, h, w, cout).permute(0, 4, 1, 2, 3)
-    return _report(f"temporal_conv b{b} f{f} {h}x{w} c{c}->{cout}", out5, ref, 2 ** -7, 1e-3)
+    return _report(f"temporal_conv b{b} f{f} {h}x{w} c{c}->{cout}", out5, ref, 2 ** -7, 1e-3, mag=mag)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -215,9 +224,10 @@ def check_temporal_attention(clips, frames, hw, heads, seed=0):
         return t.float().reshape(clips, frames, hw, heads, 64).permute(0, 2, 3, 1, 4)
     p = torch.softmax(to_seq(q) @ to_seq(k).transpose(-1, -2) * 0.125, dim=-1)
     ref = (p @ to_seq(v)).permute(0, 3, 1, 2, 4).reshape(clips * frames, hw, c)
-    out = ops.temporal_attention(q, k, v, clips, frames, hw, heads, 0.125)
+    out = ops.temporal_attention(q.reshape(-1, c), k.reshape(-1, c), v.reshape(-1, c), clips, frames, hw, heads, 0.125)
     torch.cuda.synchronize()
-    return _report(f"temporal_attention b{clips} f{frames} hw{hw} h{heads}", out, ref, 2e-2, 2e-3)
+    # 16-key softmax with O(1) values: bf16 P rounding alone gives ~4e-3 absolute error
+    return _report(f"temporal_attention b{clips} f{frames} hw{hw} h{heads}", out.reshape(ref.shape), ref, 2e-2, 6e-3)
 
 
 # ------------------------------------------------------------------------------------------------
