@@ -82,8 +82,8 @@ SIGNATURES = {
     "ca_upsample2x": [_P, _I, _I, _I, _I, _P, _P],
     "ca_router_weights": [_P, _P, _I, _I, _P, _P],
     "ca_router_merge": [_P, _P, _I, _L, _P, _P],
-    "ca_cfg_euler": [_P, _P, _P, _L, _F, _F, _F, _P, _P, _F, _P],
-    "ca_cfg_ddim": [_P, _P, _P, _L, _F, _F, _F, _P, _P, _P],
+    "ca_cfg_euler": [_P, _P, _P, _L, _F, _P, _I, _P, _P, _P],
+    "ca_cfg_ddim": [_P, _P, _P, _L, _F, _P, _I, _P, _P, _P],
     "ca_temporal_attention": [_P, _P, _P, _I, _I, _L, _I, _F, _L, _P, _P],
 }
 _RESTYPES = {"ca_last_error": C.c_char_p}

@@ -285,15 +285,15 @@ int ca_router_merge(const void* const* xs, const float* w, int32_t nactive, int6
   CA_LAUNCH(ca::launch_router_merge((const __nv_bfloat16* const*)xs, w, nactive, n, (__nv_bfloat16*)y, (cudaStream_t)s),
             "router_merge");
 }
-int ca_cfg_euler(const void* eu, const void* et, const float* lat, int64_t n, float g, float sigma, float sigma_next,
-                 float* lat_out, void* next_in, float next_scale, void* s) {
-  CA_LAUNCH(ca::launch_cfg_euler((const __nv_bfloat16*)eu, (const __nv_bfloat16*)et, lat, n, g, sigma, sigma_next, 0,
-                                 lat_out, (__nv_bfloat16*)next_in, next_scale, (cudaStream_t)s), "cfg_euler");
+int ca_cfg_euler(const void* eu, const void* et, const float* lat, int64_t n, float g, const float* step_row,
+                 int32_t round_latents_bf16, float* lat_out, void* next_in, void* s) {
+  CA_LAUNCH(ca::launch_cfg_euler((const __nv_bfloat16*)eu, (const __nv_bfloat16*)et, lat, n, g, step_row,
+                                 round_latents_bf16, lat_out, (__nv_bfloat16*)next_in, (cudaStream_t)s), "cfg_euler");
 }
-int ca_cfg_ddim(const void* eu, const void* et, const float* lat, int64_t n, float g, float a_t, float a_prev,
-                float* lat_out, void* next_in, void* s) {
-  CA_LAUNCH(ca::launch_cfg_ddim((const __nv_bfloat16*)eu, (const __nv_bfloat16*)et, lat, n, g, a_t, a_prev, lat_out,
-                                (__nv_bfloat16*)next_in, (cudaStream_t)s), "cfg_ddim");
+int ca_cfg_ddim(const void* eu, const void* et, const float* lat, int64_t n, float g, const float* step_row,
+                int32_t round_latents_bf16, float* lat_out, void* next_in, void* s) {
+  CA_LAUNCH(ca::launch_cfg_ddim((const __nv_bfloat16*)eu, (const __nv_bfloat16*)et, lat, n, g, step_row,
+                                round_latents_bf16, lat_out, (__nv_bfloat16*)next_in, (cudaStream_t)s), "cfg_ddim");
 }
 int ca_temporal_attention(const void* q, const void* k, const void* v, int32_t clips, int32_t frames, int64_t hw,
                           int32_t heads, float scale, int64_t in_row_stride, void* out, void* s) {

@@ -261,35 +261,41 @@ cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// CFG + scheduler step.  Latents are carried in fp32 between steps (the schedulers up-cast internally);
-// the next step's model input (scaled, bf16) is produced in the same pass.
+// CFG + scheduler step in one pass.  The per-step scalars come from a device row {t, a, b, c} so that the whole
+// denoising step can be captured once in a CUDA graph and replayed for every timestep.
+// Rounding points follow the reference's bf16 pipeline (latents are bf16 between steps, the scheduler up-casts
+// internally): eps = u + g*(c-u) in bf16 ops; Euler: x0 = x - bf16(sigma*eps) (0-dim fp32 sigma times a bf16
+// tensor yields bf16), d = (x-x0)/sigma, x' = bf16(x + d*(sigma_next-sigma)); next model input = bf16(x'/div).
 // ---------------------------------------------------------------------------------------------
 __global__ void cfg_euler_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
-                                 const float* __restrict__ lat, long long n, float g, float sigma, float sigma_next,
-                                 float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in, float next_scale) {
+                                 const float* __restrict__ lat, long long n, float g, const float* __restrict__ row,
+                                 int round_lat, float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
+  const float sigma = row[1], sigma_next = row[2], next_div = row[3];
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float u = __bfloat162float(eu[i]), c = __bfloat162float(et[i]);
     const float eps = round_bf16(u + round_bf16(g * round_bf16(c - u)));
     const float x = lat[i];
-    const float x0 = x - sigma * eps;
+    const float x0 = x - round_bf16(sigma * eps);
     const float d = (x - x0) / sigma;
-    const float xn = x + d * (sigma_next - sigma);
+    float xn = x + d * (sigma_next - sigma);
+    if (round_lat) xn = round_bf16(xn);
     lat_out[i] = xn;
-    if (next_in) next_in[i] = __float2bfloat16_rn(xn * next_scale);
+    if (next_in) next_in[i] = __float2bfloat16_rn(xn / next_div);
   }
 }
 cudaError_t launch_cfg_euler(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
-                             long long n, float guidance, float sigma, float sigma_next, int /*pred_type*/,
-                             float* latents_out, __nv_bfloat16* model_in_next, float next_in_scale,
-                             cudaStream_t stream) {
-  cfg_euler_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, sigma,
-                                                           sigma_next, latents_out, model_in_next, next_in_scale);
+                             long long n, float guidance, const float* step_row, int round_latents_bf16,
+                             float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream) {
+  cfg_euler_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, step_row,
+                                                           round_latents_bf16, latents_out, model_in_next);
   return cudaGetLastError();
 }
+// DDIM (eta 0, epsilon prediction): row = {t, alpha_prod_t, alpha_prod_prev, -}
 __global__ void cfg_ddim_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
-                                const float* __restrict__ lat, long long n, float g, float a_t, float a_prev,
-                                float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
+                                const float* __restrict__ lat, long long n, float g, const float* __restrict__ row,
+                                int round_lat, float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
+  const float a_t = row[1], a_prev = row[2];
   const float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), sap = sqrtf(a_prev), sbp = sqrtf(1.f - a_prev);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -297,16 +303,17 @@ __global__ void cfg_ddim_kernel(const __nv_bfloat16* __restrict__ eu, const __nv
     const float eps = round_bf16(u + round_bf16(g * round_bf16(c - u)));
     const float x = lat[i];
     const float x0 = (x - sb * eps) / sa;
-    const float xn = sap * x0 + sbp * eps;
+    float xn = sap * x0 + sbp * eps;
+    if (round_lat) xn = round_bf16(xn);
     lat_out[i] = xn;
     if (next_in) next_in[i] = __float2bfloat16_rn(xn);
   }
 }
 cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
-                            long long n, float guidance, float alpha_t, float alpha_prev, float* latents_out,
-                            __nv_bfloat16* model_in_next, cudaStream_t stream) {
-  cfg_ddim_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, alpha_t,
-                                                          alpha_prev, latents_out, model_in_next);
+                            long long n, float guidance, const float* step_row, int round_latents_bf16,
+                            float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream) {
+  cfg_ddim_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, step_row,
+                                                          round_latents_bf16, latents_out, model_in_next);
   return cudaGetLastError();
 }
 

@@ -79,12 +79,11 @@ cudaError_t launch_router_weights(const float* logits, const unsigned char* mask
 cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, int nactive, long long n,
                                 __nv_bfloat16* y, cudaStream_t stream);
 cudaError_t launch_cfg_euler(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
-                             long long n, float guidance, float sigma, float sigma_next, int pred_type,
-                             float* latents_out, __nv_bfloat16* model_in_next, float next_in_scale,
-                             cudaStream_t stream);
+                             long long n, float guidance, const float* step_row, int round_latents_bf16,
+                             float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream);
 cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
-                            long long n, float guidance, float alpha_t, float alpha_prev, float* latents_out,
-                            __nv_bfloat16* model_in_next, cudaStream_t stream);
+                            long long n, float guidance, const float* step_row, int round_latents_bf16,
+                            float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream);
 cudaError_t launch_temporal_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
                                       int clips, int frames, long long hw, int heads, float scale,
                                       long long in_row_stride, __nv_bfloat16* out, cudaStream_t stream);

@@ -36,6 +36,55 @@ def _req(t: torch.Tensor, dtype=BF16):
 
 
 # ----------------------------------------------------------------------------------------------
+# launch accounting: every kernel launch goes through _launch(); PROFILER (off by default) brackets each launch
+# with CUDA events on the launching stream and records algorithmic FLOPs / bytes per kernel family, which is what
+# bench.py's roofline block is computed from.
+# ----------------------------------------------------------------------------------------------
+class _Profiler:
+    def __init__(self):
+        self.active = False
+        self.launches = 0
+        self.records = []
+
+    def start(self):
+        self.records = []
+        self.active = True
+
+    def stop(self):
+        self.active = False
+
+    def summary(self):
+        """-> {family: {"launches", "ms", "flops", "bytes"}} (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for fam, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+PROFILER = _Profiler()
+
+
+def _launch(fam: str, flops: float, nbytes: float, name: str, *args):
+    lib = _lib.load()
+    PROFILER.launches += 1
+    if PROFILER.active:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = getattr(lib, name)(*args)
+        e1.record()
+        PROFILER.records.append((fam, flops, nbytes, e0, e1))
+    else:
+        st = getattr(lib, name)(*args)
+    check(st, name)
+
+
+# ----------------------------------------------------------------------------------------------
 # weight packing (host side, once at load time)
 # ----------------------------------------------------------------------------------------------
 def pack_conv_weight(w: torch.Tensor, k_pad_to: int = 8) -> torch.Tensor:
@@ -156,7 +205,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         rvs = None
     _fill_epilogue(d, bias=bias, act=act, out_scale=out_scale, rowvec=rowvec, rowvec_strides=rvs, residual=residual,
                    blend_src=blend_src, res_strides=rs, blend_alpha=blend_alpha)
-    check(_lib.load().ca_gemm(C.byref(d), _stream()), "ca_gemm(linear)")
+    _launch("gemm", 2.0 * m * k * wr, 2.0 * (m * k + wr * k + m * n_out), "ca_gemm", C.byref(d), _stream())
     return out
 
 
@@ -231,7 +280,8 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
     _fill_epilogue(d, bias=bias, act=act, out_scale=out_scale, rowvec=rowvec, rowvec_strides=rvs if rowvec is not None else None,
                    residual=residual, blend_src=blend_src,
                    res_strides=os_ if (residual is not None or blend_src is not None) else None, blend_alpha=blend_alpha)
-    check(_lib.load().ca_gemm(C.byref(d), _stream()), "ca_gemm(conv2d)")
+    _launch("gemm", 2.0 * n * ho * wo * ntaps * (c + c2) * cout,
+            2.0 * (n * h * w_ * (c + c2) + w_packed.numel() + n * ho * wo * cout), "ca_gemm", C.byref(d), _stream())
     return out
 
 
@@ -270,7 +320,7 @@ def temporal_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.
                    residual=residual,
                    blend_src=blend_src, res_strides=os_ if (residual is not None or blend_src is not None) else None,
                    blend_alpha=blend_alpha)
-    check(_lib.load().ca_gemm(C.byref(d), _stream()), "ca_gemm(temporal_conv)")
+    _launch("gemm", 2.0 * bf * hw * 3 * c * cout, 2.0 * (bf * hw * (c + cout) + w_packed.numel()), "ca_gemm", C.byref(d), _stream())
     return out
 
 
@@ -294,7 +344,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hea
     d.k_row_stride, d.k_batch_stride = k.stride(1), k.stride(0)
     d.v_row_stride, d.v_batch_stride = v.stride(1), v.stride(0)
     d.out_row_stride, d.out_batch_stride = out.stride(1), out.stride(0)
-    check(_lib.load().ca_attention(C.byref(d), _stream()), "ca_attention")
+    _launch("attention", 4.0 * b * heads * lq * lk * head_dim_pad, 2.0 * b * (2 * lq + 2 * lk) * ctot, "ca_attention", C.byref(d), _stream())
     return out
 
 
@@ -305,8 +355,8 @@ def temporal_attention(q, k, v, clips: int, frames: int, hw: int, heads: int, sc
     rs = c if row_stride is None else row_stride
     if out is None:
         out = torch.empty((clips * frames * hw, c), device=q.device, dtype=BF16)
-    check(_lib.load().ca_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), clips, frames, hw, heads,
-                                            float(scale), rs, out.data_ptr(), _stream()), "ca_temporal_attention")
+    _launch("temporal_attention", 4.0 * clips * hw * heads * frames * frames * 64, 2.0 * 4 * clips * frames * hw * c, "ca_temporal_attention", q.data_ptr(), k.data_ptr(), v.data_ptr(), clips, frames, hw, heads,
+                                            float(scale), rs, out.data_ptr(), _stream())
     return out
 
 
@@ -335,16 +385,15 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     n, h, w_, c = x.shape
     c2 = x2.shape[3] if x2 is not None else 0
     ct = c + c2
-    lib = _lib.load()
     nsamp = n // imgs_per_sample
     sums = torch.empty(nsamp * groups * 2, device=x.device, dtype=torch.float64)
-    check(lib.ca_groupnorm_stats(x.data_ptr(), c, _ptr(x2), c2, nsamp, imgs_per_sample * h * w_, groups,
-                                 sums.data_ptr(), _stream()), "ca_groupnorm_stats")
+    _launch("groupnorm", 0.0, 2.0 * n * h * w_ * ct, "ca_groupnorm_stats", x.data_ptr(), c, _ptr(x2), c2, nsamp,
+            imgs_per_sample * h * w_, groups, sums.data_ptr(), _stream())
     if out is None:
         out = torch.empty((n, h * 2, w_ * 2, ct) if up2x else (n, h, w_, ct), device=x.device, dtype=BF16)
-    check(lib.ca_groupnorm_apply(x.data_ptr(), c, _ptr(x2), c2, n, h, w_, imgs_per_sample, groups, float(eps),
-                                 sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(silu), int(up2x),
-                                 out.data_ptr(), _stream()), "ca_groupnorm_apply")
+    _launch("groupnorm", 0.0, 2.0 * n * h * w_ * ct * (5 if up2x else 2), "ca_groupnorm_apply", x.data_ptr(), c,
+            _ptr(x2), c2, n, h, w_, imgs_per_sample, groups, float(eps), sums.data_ptr(), gamma.data_ptr(),
+            beta.data_ptr(), int(silu), int(up2x), out.data_ptr(), _stream())
     return out
 
 
@@ -355,9 +404,8 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     rows = x.numel() // c
     y = torch.empty_like(x)
     ysum = torch.empty_like(x) if (add_rowvec is not None and return_sum) else None
-    check(_lib.load().ca_layernorm(x.data_ptr(), rows, c, float(eps), gamma.data_ptr(), beta.data_ptr(),
-                                   _ptr(add_rowvec), rows_per_vec, _ptr(ysum), y.data_ptr(), _stream()),
-          "ca_layernorm")
+    _launch("layernorm", 0.0, 2.0 * 2 * x.numel(), "ca_layernorm", x.data_ptr(), rows, c, float(eps), gamma.data_ptr(), beta.data_ptr(),
+                                   _ptr(add_rowvec), rows_per_vec, _ptr(ysum), y.data_ptr(), _stream())
     return (y, ysum) if return_sum else y
 
 
@@ -369,22 +417,22 @@ def timestep_embedding(t: torch.Tensor, dim: int, *, flip_sin_to_cos: bool = Tru
     _req(t, torch.float32)
     n = t.numel()
     out = torch.empty((n, dim), device=t.device, dtype=BF16)
-    check(_lib.load().ca_timestep_embedding(t.data_ptr(), n, dim, int(flip_sin_to_cos), float(freq_shift),
-                                            int(round_t_bf16), out.data_ptr(), _stream()), "ca_timestep_embedding")
+    _launch("timestep_embedding", 0.0, 0.0, "ca_timestep_embedding", t.data_ptr(), n, dim, int(flip_sin_to_cos), float(freq_shift),
+                                            int(round_t_bf16), out.data_ptr(), _stream())
     return out
 
 
 def silu(x: torch.Tensor):
     _req(x)
     y = torch.empty_like(x)
-    check(_lib.load().ca_silu(x.data_ptr(), x.numel(), y.data_ptr(), _stream()), "ca_silu")
+    _launch("silu", 0.0, 2.0 * 2 * x.numel(), "ca_silu", x.data_ptr(), x.numel(), y.data_ptr(), _stream())
     return y
 
 
 def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None):
     _req(a); _req(b)
     y = torch.empty_like(a) if out is None else out
-    check(_lib.load().ca_add(a.data_ptr(), b.data_ptr(), a.numel(), y.data_ptr(), _stream()), "ca_add")
+    _launch("add", 0.0, 2.0 * 3 * a.numel(), "ca_add", a.data_ptr(), b.data_ptr(), a.numel(), y.data_ptr(), _stream())
     return y
 
 
@@ -397,8 +445,8 @@ def nchw_to_nhwc(x: torch.Tensor, c_pad: Optional[int] = None):
     y = torch.empty((n, h, w_, cp), device=x.device, dtype=BF16)
     if x.dtype not in (BF16, torch.float32):
         raise ValueError("nchw_to_nhwc: bf16 or fp32 input")
-    check(_lib.load().ca_nchw_to_nhwc(x.data_ptr(), int(x.dtype == torch.float32), n, c, h * w_, cp, y.data_ptr(),
-                                      _stream()), "ca_nchw_to_nhwc")
+    _launch("nchw_to_nhwc", 0.0, 2.0 * 2 * x.numel(), "ca_nchw_to_nhwc", x.data_ptr(), int(x.dtype == torch.float32), n, c, h * w_, cp, y.data_ptr(),
+                                      _stream())
     return y
 
 
@@ -407,8 +455,7 @@ def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None, fp32: bool = False):
     n, h, w_, cs = x.shape
     cc = cs if c is None else c
     y = torch.empty((n, cc, h, w_), device=x.device, dtype=torch.float32 if fp32 else BF16)
-    check(_lib.load().ca_nhwc_to_nchw(x.data_ptr(), n, cc, cs, h * w_, y.data_ptr(), int(fp32), _stream()),
-          "ca_nhwc_to_nchw")
+    _launch("nhwc_to_nchw", 0.0, 2.0 * 2 * x.numel(), "ca_nhwc_to_nchw", x.data_ptr(), n, cc, cs, h * w_, y.data_ptr(), int(fp32), _stream())
     return y
 
 
@@ -416,7 +463,7 @@ def avgpool(x: torch.Tensor, oh: int, ow: int):
     _req(x)
     n, h, w_, c = x.shape
     y = torch.empty((n, oh, ow, c), device=x.device, dtype=BF16)
-    check(_lib.load().ca_avgpool(x.data_ptr(), n, h, w_, c, oh, ow, y.data_ptr(), _stream()), "ca_avgpool")
+    _launch("avgpool", 0.0, 2.0 * x.numel(), "ca_avgpool", x.data_ptr(), n, h, w_, c, oh, ow, y.data_ptr(), _stream())
     return y
 
 
@@ -424,7 +471,7 @@ def upsample2x(x: torch.Tensor):
     _req(x)
     n, h, w_, c = x.shape
     y = torch.empty((n, 2 * h, 2 * w_, c), device=x.device, dtype=BF16)
-    check(_lib.load().ca_upsample2x(x.data_ptr(), n, h, w_, c, y.data_ptr(), _stream()), "ca_upsample2x")
+    _launch("upsample2x", 0.0, 2.0 * 5 * x.numel(), "ca_upsample2x", x.data_ptr(), n, h, w_, c, y.data_ptr(), _stream())
     return y
 
 
@@ -433,8 +480,7 @@ def router_weights(logits: torch.Tensor, mask: Optional[torch.Tensor]):
     _req(logits, torch.float32)
     r, e = logits.shape
     out = torch.empty_like(logits)
-    check(_lib.load().ca_router_weights(logits.data_ptr(), _ptr(mask), r, e, out.data_ptr(), _stream()),
-          "ca_router_weights")
+    _launch("router_weights", 0.0, 0.0, "ca_router_weights", logits.data_ptr(), _ptr(mask), r, e, out.data_ptr(), _stream())
     return out
 
 
@@ -446,27 +492,30 @@ def router_merge(xs: Sequence[torch.Tensor], w: torch.Tensor, ptr_table: Optiona
     if ptr_table is None:
         ptr_table = torch.tensor([x.data_ptr() for x in xs], dtype=torch.int64).to(xs[0].device)
     y = torch.empty_like(xs[0])
-    check(_lib.load().ca_router_merge(ptr_table.data_ptr(), w.data_ptr(), len(xs), xs[0].numel(), y.data_ptr(),
-                                      _stream()), "ca_router_merge")
+    _launch("router_merge", 0.0, 2.0 * (len(xs) + 1) * xs[0].numel(), "ca_router_merge", ptr_table.data_ptr(), w.data_ptr(), len(xs), xs[0].numel(), y.data_ptr(),
+                                      _stream())
     return y
 
 
-def cfg_euler(eps_uncond, eps_text, latents, guidance, sigma, sigma_next, next_in_scale, latents_out=None,
-              model_in_next=None):
-    _req(eps_uncond); _req(eps_text); _req(latents, torch.float32)
+def cfg_euler(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None, model_in_next=None,
+              round_latents_bf16: bool = True):
+    """step_row: device fp32 [4] = (t, sigma, sigma_next, sqrt(sigma_next^2+1))."""
+    _req(eps_uncond); _req(eps_text); _req(latents, torch.float32); _req(step_row, torch.float32)
     if latents_out is None:
         latents_out = torch.empty_like(latents)
-    check(_lib.load().ca_cfg_euler(eps_uncond.data_ptr(), eps_text.data_ptr(), latents.data_ptr(), latents.numel(),
-                                   float(guidance), float(sigma), float(sigma_next), latents_out.data_ptr(),
-                                   _ptr(model_in_next), float(next_in_scale), _stream()), "ca_cfg_euler")
+    _launch("cfg_euler", 0.0, 0.0, "ca_cfg_euler", eps_uncond.data_ptr(), eps_text.data_ptr(), latents.data_ptr(), latents.numel(),
+                                   float(guidance), step_row.data_ptr(), int(round_latents_bf16),
+                                   latents_out.data_ptr(), _ptr(model_in_next), _stream())
     return latents_out
 
 
-def cfg_ddim(eps_uncond, eps_text, latents, guidance, alpha_t, alpha_prev, latents_out=None, model_in_next=None):
-    _req(eps_uncond); _req(eps_text); _req(latents, torch.float32)
+def cfg_ddim(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None, model_in_next=None,
+             round_latents_bf16: bool = True):
+    """step_row: device fp32 [4] = (t, alpha_prod_t, alpha_prod_prev, -)."""
+    _req(eps_uncond); _req(eps_text); _req(latents, torch.float32); _req(step_row, torch.float32)
     if latents_out is None:
         latents_out = torch.empty_like(latents)
-    check(_lib.load().ca_cfg_ddim(eps_uncond.data_ptr(), eps_text.data_ptr(), latents.data_ptr(), latents.numel(),
-                                  float(guidance), float(alpha_t), float(alpha_prev), latents_out.data_ptr(),
-                                  _ptr(model_in_next), _stream()), "ca_cfg_ddim")
+    _launch("cfg_ddim", 0.0, 0.0, "ca_cfg_ddim", eps_uncond.data_ptr(), eps_text.data_ptr(), latents.data_ptr(), latents.numel(),
+                                  float(guidance), step_row.data_ptr(), int(round_latents_bf16),
+                                  latents_out.data_ptr(), _ptr(model_in_next), _stream())
     return latents_out

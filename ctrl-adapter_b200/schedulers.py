@@ -1,0 +1,68 @@
+"""Host-side schedule tables for the fused CFG + scheduler kernels (tiny numpy math, done once per generation).
+
+EulerDiscrete: the SDXL-base default scheduler used by the reference SDXL pipeline
+(/root/reference/sdxl/pipelines/sdxl_controlnet_adapter_pipeline.py:1169,1285,1378; diffusers v0.27.2
+EulerDiscreteScheduler with scaled_linear betas 0.00085..0.012, 1000 train steps, timestep_spacing="leading",
+steps_offset=1, epsilon prediction, linear sigma interpolation).
+DDIM: I2VGen-XL pipeline (/root/reference/i2vgen_xl/pipelines/i2vgen_xl_controlnet_adapter_pipeline.py:1112).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _alphas_cumprod(beta_start=0.00085, beta_end=0.012, n=1000, schedule="scaled_linear"):
+    if schedule == "scaled_linear":
+        betas = np.linspace(beta_start ** 0.5, beta_end ** 0.5, n, dtype=np.float32) ** 2
+    elif schedule == "linear":
+        betas = np.linspace(beta_start, beta_end, n, dtype=np.float32)
+    else:
+        raise ValueError(schedule)
+    return np.cumprod(1.0 - betas, axis=0)
+
+
+class EulerDiscreteSchedule:
+    def __init__(self, num_inference_steps: int, num_train_timesteps: int = 1000, steps_offset: int = 1):
+        ac = _alphas_cumprod(n=num_train_timesteps)
+        step_ratio = num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.float32) + steps_offset
+        sig = ((1 - ac) / ac) ** 0.5
+        sig = np.interp(ts, np.arange(0, len(sig)), sig).astype(np.float32)
+        self.timesteps = ts                                   # fed to ControlNet / adapter / UNet
+        self.sigmas = np.concatenate([sig, [0.0]]).astype(np.float32)
+        self.init_noise_sigma = float((self.sigmas.max() ** 2 + 1) ** 0.5)  # "leading" spacing
+
+    def input_scale(self, i: int) -> float:
+        """scale_model_input: sample / sqrt(sigma_i^2 + 1)"""
+        return float(1.0 / (self.sigmas[i] ** 2 + 1) ** 0.5)
+
+    def table(self):
+        """[steps, 4] fp32 rows (t, sigma, sigma_next, sqrt(sigma_next^2 + 1)) consumed by ca_cfg_euler; the last
+        entry is the scale_model_input divisor of the NEXT step's model input (1 after the final step)."""
+        n = len(self.timesteps)
+        rows = np.zeros((n, 4), dtype=np.float32)
+        for i in range(n):
+            rows[i] = (self.timesteps[i], self.sigmas[i], self.sigmas[i + 1],
+                       np.sqrt(np.float32(self.sigmas[i + 1]) ** 2 + np.float32(1.0)))
+        return rows
+
+
+class DDIMSchedule:
+    """DDIM, eta = 0, epsilon prediction, "leading" spacing, steps_offset 1, no sample clipping."""
+
+    def __init__(self, num_inference_steps: int, num_train_timesteps: int = 1000, steps_offset: int = 1,
+                 beta_schedule: str = "scaled_linear", set_alpha_to_one: bool = False):
+        self.ac = _alphas_cumprod(n=num_train_timesteps, schedule=beta_schedule)
+        step_ratio = num_train_timesteps // num_inference_steps
+        self.timesteps = ((np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
+                          + steps_offset)
+        self.step_ratio = step_ratio
+        self.final_alpha = 1.0 if set_alpha_to_one else float(self.ac[0])
+        self.init_noise_sigma = 1.0
+
+    def table(self):
+        rows = np.zeros((len(self.timesteps), 4), dtype=np.float32)
+        for i, t in enumerate(self.timesteps):
+            prev = t - self.step_ratio
+            rows[i] = (t, self.ac[t], self.ac[prev] if prev >= 0 else self.final_alpha, 1.0)
+        return rows

@@ -166,16 +166,19 @@ int ca_router_weights(const float* logits, const uint8_t* mask, int32_t nrouters
  * after each multiply and each add as in the reference loop.  xs: device array of nactive pointers. */
 int ca_router_merge(const void* const* xs, const float* w, int32_t nactive, int64_t n, void* y, void* cuda_stream);
 
-/* Classifier-free guidance + scheduler update in one pass.
- * Euler (SDXL default EulerDiscreteScheduler, epsilon prediction; sdxl pipeline :1369-1378):
- *   eps = u + g (c - u); x0 = x - sigma*eps; d = (x - x0)/sigma; x' = x + d (sigma_next - sigma)
- *   also emits the next step's scaled model input  x' * next_in_scale  in bf16.
- * DDIM (I2VGen-XL; i2vgen_xl pipeline :1102-1115), eta = 0, epsilon prediction. */
+/* Classifier-free guidance + scheduler update in one pass (latent-sized, HBM-bound).
+ * `step_row` is a DEVICE pointer to 4 floats so that a captured CUDA graph of the step can be replayed for every
+ * timestep:  Euler {t, sigma, sigma_next, sqrt(sigma_next^2+1)}   DDIM {t, alpha_prod_t, alpha_prod_prev, -}.
+ * Euler = SDXL default EulerDiscreteScheduler, epsilon prediction (sdxl pipeline :1369-1378):
+ *   eps = u + g (c - u); x0 = x - sigma*eps; d = (x - x0)/sigma; x' = x + d (sigma_next - sigma);
+ *   also emits the next step's scaled model input x' / sqrt(sigma_next^2+1) in bf16 (scale_model_input, :1285).
+ * DDIM = I2VGen-XL (i2vgen_xl pipeline :1102-1115), eta = 0, epsilon prediction.
+ * round_latents_bf16 = 1 reproduces the reference's bf16 latents between steps. */
 int ca_cfg_euler(const void* eps_uncond, const void* eps_text, const float* latents_in, int64_t n, float guidance,
-                 float sigma, float sigma_next, float* latents_out, void* model_in_next, float next_in_scale,
+                 const float* step_row, int32_t round_latents_bf16, float* latents_out, void* model_in_next,
                  void* cuda_stream);
 int ca_cfg_ddim(const void* eps_uncond, const void* eps_text, const float* latents_in, int64_t n, float guidance,
-                float alpha_prod_t, float alpha_prod_prev, float* latents_out, void* model_in_next,
+                const float* step_row, int32_t round_latents_bf16, float* latents_out, void* model_in_next,
                 void* cuda_stream);
 
 /*

@@ -5,7 +5,9 @@ stand-alone report:  python -m tests.kernel_checks  [--json out.json]
 Tolerances (stated per check, torch.testing semantics |out-ref| <= atol + rtol*|ref|):
   * fp32-output contractions: rtol 1e-3 / atol 1e-4 (north-star tolerance; fp32 accumulate on both sides)
   * bf16-output kernels: the fp32 reference is rounded to bf16 the same way; allowance = 1 bf16 ulp
-    (rtol 2^-7) + atol 1e-3 for values that straddle a rounding boundary after a different summation order
+    (rtol 2^-7) + atol 1e-3 for values that straddle a rounding boundary after a different summation order;
+    epilogues with several rounding steps (conv -> +temb -> +residual) get 2 ulps (rtol 2^-6) of the largest
+    intermediate magnitude, since two independent boundary flips can stack
   * attention: P is rounded to bf16 before the PV product (as in flash-attention / SDPA): rtol 2e-2 / atol 2e-3,
     and the error must not exceed 2x that of torch's own bf16 SDPA against the same fp32 reference.
 """
@@ -82,7 +84,7 @@ def check_linear(m, k, n, *, bn=0, bias=True, out_fp32=True, residual=False, act
     out = ops.linear(x, w, ops.bias_f32(b), act=ops.ACT_SILU if act == "silu" else ops.ACT_NONE, residual=res,
                      out_fp32=out_fp32, bn=bn)
     torch.cuda.synchronize()
-    rtol, atol = (1e-3, 1e-4) if out_fp32 else (2 ** -7, 1e-3)
+    rtol, atol = (1e-3, 1e-4) if out_fp32 else (2 ** -6 if residual else 2 ** -7, 1e-3)
     return _report(f"linear m{m} k{k} n{n} bn{bn} {'f32' if out_fp32 else 'bf16'} act={act} res={int(residual)}",
                    out, ref, rtol, atol, mag=mag)
 
@@ -110,7 +112,7 @@ def check_linear_rowvec(m, k, n, rpv, seed=0):
     ref = (lin + rv.float().repeat_interleave(rpv, dim=0)).to(BF16).float()
     out = ops.linear(x, w, None, rowvec=rv, rows_per_vec=rpv)
     torch.cuda.synchronize()
-    return _report(f"linear+rowvec m{m} k{k} n{n} rpv{rpv}", out, ref, 2 ** -7, 1e-3, mag=lin)
+    return _report(f"linear+rowvec m{m} k{k} n{n} rpv{rpv}", out, ref, 2 ** -6, 1e-3, mag=lin)
 
 
 def check_linear_blend(m, k, n, seed=0):
@@ -164,7 +166,7 @@ def check_conv(n, h, w, cin, cout, *, ksize=3, stride=1, cin2=0, out_fp32=True, 
     out = ops.conv2d(_nhwc(x), wp, ops.bias_f32(b), ksize=ksize, stride=stride, x2=_nhwc(x2) if x2 is not None else None,
                      out_fp32=out_fp32, rowvec=rv, residual=_nhwc(res) if res is not None else None, out_scale=scale)
     torch.cuda.synchronize()
-    rtol, atol = (1e-3, 1e-4) if out_fp32 else (2 ** -7, 1e-3)
+    rtol, atol = (1e-3, 1e-4) if out_fp32 else (2 ** -6 if (rowvec or residual) else 2 ** -7, 1e-3)
     return _report(f"conv{ksize}x{ksize} s{stride} n{n} {h}x{w} c{cin}+{cin2}->{cout} {'f32' if out_fp32 else 'bf16'}"
                    f" rv={int(rowvec)} res={int(residual)} sc={scale}", out.permute(0, 3, 1, 2), ref, rtol, atol, mag=mag)
 
@@ -182,7 +184,7 @@ def check_temporal_conv(b, f, h, w, c, cout, seed=0):
     out = ops.temporal_conv(xl, ops.pack_conv_weight(wt), ops.bias_f32(bias), f, rowvec=rv)
     torch.cuda.synchronize()
     out5 = out.reshape(b, f, h, w, cout).permute(0, 4, 1, 2, 3)
-    return _report(f"temporal_conv b{b} f{f} {h}x{w} c{c}->{cout}", out5, ref, 2 ** -7, 1e-3, mag=mag)
+    return _report(f"temporal_conv b{b} f{f} {h}x{w} c{c}->{cout}", out5, ref, 2 ** -6, 1e-3, mag=mag)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -338,22 +340,26 @@ def check_router(seed=0):
 def check_cfg(seed=0):
     ops = _ops()
     eu, et = _rand(2, 4, 16, 16, seed=seed + 1), _rand(2, 4, 16, 16, seed=seed + 2)
-    lat = _rand(2, 4, 16, 16, seed=seed + 3, dtype=torch.float32)
+    lat = _rand(2, 4, 16, 16, seed=seed + 3, dtype=torch.float32).to(BF16).float()
     g, sigma, sigma_next = 5.0, 3.2, 2.7
-    eps = (eu + (g * (et - eu)).to(BF16)).to(BF16).float()
-    x0 = lat - sigma * eps
-    ref = lat + (lat - x0) / sigma * (sigma_next - sigma)
+    div = math.sqrt(sigma_next ** 2 + 1)
+    row = torch.tensor([981.0, sigma, sigma_next, div], device="cuda")
+    eps = (eu + (g * (et - eu)).to(BF16)).to(BF16)
+    x0 = lat - (torch.tensor(sigma, device="cuda") * eps).float()  # 0-dim fp32 * bf16 tensor -> bf16
+    ref = (lat + (lat - x0) / sigma * (sigma_next - sigma)).to(BF16)
     nxt = torch.empty_like(eu)
-    out = ops.cfg_euler(eu, et, lat, g, sigma, sigma_next, 0.5, model_in_next=nxt)
+    out = ops.cfg_euler(eu, et, lat, g, row, model_in_next=nxt)
     torch.cuda.synchronize()
-    _report("cfg_euler", out, ref, 1e-5, 1e-5)
-    _report("cfg_euler next_in", nxt, (ref * 0.5).to(BF16), 2 ** -7, 1e-3)
+    _report("cfg_euler (bf16 latents)", out, ref, 2 ** -7, 1e-3)
+    _report("cfg_euler next_in", nxt, (ref / torch.tensor(div, device="cuda")).to(BF16), 2 ** -7, 1e-3)
     a_t, a_prev = 0.3, 0.45
-    x0 = (lat - math.sqrt(1 - a_t) * eps) / math.sqrt(a_t)
-    ref = math.sqrt(a_prev) * x0 + math.sqrt(1 - a_prev) * eps
-    out = ops.cfg_ddim(eu, et, lat, g, a_t, a_prev)
+    row = torch.tensor([500.0, a_t, a_prev, 1.0], device="cuda")
+    epsf = eps.float()
+    x0 = (lat - math.sqrt(1 - a_t) * epsf) / math.sqrt(a_t)
+    ref = math.sqrt(a_prev) * x0 + math.sqrt(1 - a_prev) * epsf
+    out = ops.cfg_ddim(eu, et, lat, g, row, round_latents_bf16=False)
     torch.cuda.synchronize()
-    _report("cfg_ddim", out, ref, 1e-5, 1e-5)
+    _report("cfg_ddim (fp32 latents)", out, ref, 1e-5, 1e-5)
 
 
 # ------------------------------------------------------------------------------------------------
