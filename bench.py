@@ -302,6 +302,11 @@ def main():
         loop.step(0)
         ops.PROFILER.stop()
         fam = ops.PROFILER.summary()
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump(ops.PROFILER.launches_table(80), open(os.path.join(ROOT, "gpurun_out", "launch_table.json"), "w"), indent=0)
+        except Exception:
+            pass
         tot = sum(v["ms"] for v in fam.values())
         families = {k: {"launches": v["launches"], "ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4),
                         "tflops": round(v["flops"] / (v["ms"] * 1e9), 2) if v["ms"] > 0 and v["flops"] else None,

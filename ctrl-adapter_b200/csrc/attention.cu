@@ -27,7 +27,10 @@ struct AttnCfg {
   static constexpr uint32_t kQBytes = DQ * kChunkBytes;
   static constexpr uint32_t kPBytes = 2 * kChunkBytes;
   static constexpr uint32_t kStageBytes = (DQ + 1) * kChunkBytes;  // K chunks + one V slice
-  static constexpr uint32_t kSmemBytes = kQBytes + kPBytes + kStages * kStageBytes + 1024 + 128;
+  // data + 1024: the slack serves both the 1024-byte alignment of the swizzled tiles and the 88 bytes of mbarriers.
+  // For DQ == 1 this is 115712 B, i.e. exactly two CTAs per SM: 2 x (115712 + 1024 reserved) = 233472 = 228 KB.
+  static constexpr uint32_t kDataBytes = kQBytes + kPBytes + kStages * kStageBytes;
+  static constexpr uint32_t kSmemBytes = kDataBytes + 1024;
   static constexpr uint32_t kTmemCols = 256;
 };
 
@@ -44,7 +47,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   using Cfg = AttnCfg<DQ>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  if (pad + Cfg::kDataBytes + 128 > Cfg::kSmemBytes) __trap();  // barriers would not fit behind the tiles
   uint8_t* smem_q = smem;
   uint8_t* smem_p = smem + Cfg::kQBytes;
   uint8_t* smem_kv = smem_p + Cfg::kPBytes;

@@ -270,13 +270,16 @@ cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, 
 __global__ void cfg_euler_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
                                  const float* __restrict__ lat, long long n, float g, const float* __restrict__ row,
                                  int round_lat, float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
-  const float sigma = row[1], sigma_next = row[2], next_div = row[3];
+  // A 0-dim fp32 tensor combined with a bf16 tensor is first cast to bf16 by PyTorch's type promotion, so the
+  // reference multiplies eps by bf16(sigma) and divides the next model input by bf16(sqrt(sigma_next^2+1)).
+  const float sigma = row[1], sigma_next = row[2], next_div = round_bf16(row[3]);
+  const float sigma_b = round_bf16(sigma);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float u = __bfloat162float(eu[i]), c = __bfloat162float(et[i]);
     const float eps = round_bf16(u + round_bf16(g * round_bf16(c - u)));
     const float x = lat[i];
-    const float x0 = x - round_bf16(sigma * eps);
+    const float x0 = x - round_bf16(sigma_b * eps);
     const float d = (x - x0) / sigma;
     float xn = x + d * (sigma_next - sigma);
     if (round_lat) xn = round_bf16(xn);

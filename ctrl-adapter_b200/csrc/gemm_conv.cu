@@ -9,11 +9,14 @@
 // hardware zero fill outside the tensor -- i.e. implicit-GEMM convolution with no
 // im2col buffer.  Weights are [N][taps*K] bf16 (K contiguous).
 //
-// Structure (persistent, warp specialised, one CTA per SM):
-//   warp 0  : TMA producer  (A box + W tile per k-iteration into a 4-stage smem ring)
-//   warp 1  : MMA issuer    (single thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16)
-//   warp 2  : TMEM allocator
-//   warps 4-7: epilogue     (tcgen05.ld -> bias / temb / SiLU / GEGLU / scale / residual / blend -> bf16 store)
+// Structure (persistent, warp specialised, one CTA per SM, 384 threads):
+//   warp 0    : TMA producer  (A box + W tile per k-iteration into a multi-stage smem ring)
+//   warp 1    : MMA issuer    (single thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16)
+//   warp 2    : TMEM allocator
+//   warps 4-11: epilogue.  Warp e owns TMEM lane quarter (e & 3) and every second 64-column unit (e >> 2):
+//               tcgen05.ld -> bias / SiLU / GEGLU / scale / temb / residual / blend (bf16 rounding after each step,
+//               mirroring the autocast rounding points) -> warp-private swizzled smem staging -> 128-byte
+//               coalesced global stores.  Residual tiles are read through the same staging buffer.
 // Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "kernels.h"
@@ -22,7 +25,10 @@ namespace ca {
 
 static constexpr int kBM = 128;
 static constexpr int kBK = 64;
-static constexpr int kGemmThreads = 256;
+static constexpr int kEpiWarps = 8;
+static constexpr int kGemmThreads = 128 + kEpiWarps * 32;  // 384
+static constexpr uint32_t kStageRowBytes = 128;            // 64 bf16 columns per staged row
+static constexpr uint32_t kStagingBytes = kEpiWarps * 32 * kStageRowBytes;  // 32 KB
 
 template <int BN>
 struct GemmCfg {
@@ -32,7 +38,24 @@ struct GemmCfg {
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kTmemCols = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);  // 2 accumulator stages
   static constexpr uint32_t kAccStride = kTmemCols / 2;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// erf with |error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26) -- far below the bf16 rounding applied to GELU's output
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(e, x);
+}
+
+struct RowInfo {
+  long long out_off, res_off, rv_off;
+  bool ok;
 };
 
 template <int BN>
@@ -46,7 +69,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
 
   uint8_t* smem_a = smem;                                    // kStages x 16 KB
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;      // kStages x BN*128 B
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stage = smem + Cfg::kStages * Cfg::kStageBytes;  // kEpiWarps x 4 KB epilogue staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage + kStagingBytes);
   uint64_t* full_bar = bars;                     // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;     // [kStages]
   uint64_t* acc_full = bars + 2 * Cfg::kStages;  // [2]
@@ -74,7 +98,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[a], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -148,16 +172,22 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;       // row of the tile owned by this thread
+    const int ew = warp - 4;           // 0..7
+    const int q = warp & 3;            // TMEM lane quarter this warp may access (== warp id % 4)
+    const int half_sel = ew >> 2;      // which of every two 64-column units this warp processes
+    const int r = q * 32 + lane;       // tile row owned by this thread
     const bool geglu = (p.act == CA_ACT_GEGLU);
     const int ncols_out = geglu ? BN / 2 : BN;  // output columns produced per tile
+    uint8_t* stg = smem_stage + ew * (32 * kStageRowBytes);  // warp-private [32 rows][128 B], 16-byte units XOR-swizzled
     float alpha_s = 0.f, alpha_t = 0.f;
     if (p.blend_src != nullptr) {
       const float a = *p.blend_alpha;  // bf16-valued
       alpha_s = a;
       alpha_t = round_bf16(1.0f - a);
     }
+    // copy-in / copy-out role of this lane: row (it*4 + lane/8) of the warp's 32 rows, 16-byte segment lane%8
+    const int seg = lane & 7;
+    const int rsub = lane >> 3;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -179,58 +209,77 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
       const long long rv_off = (p.rowvec != nullptr)
                                    ? (o[0] * p.vstride[0] + o[1] * p.vstride[1] + o[2] * p.vstride[2] + o[3] * p.vstride[3])
                                    : 0;
+      const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
       const int col_base = tn * ncols_out;  // first output column of this tile
 
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + acc * Cfg::kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 
-      for (int c0 = 0; c0 < ncols_out; c0 += 32) {
-        if (col_base + c0 >= p.n_out) break;  // whole chunk beyond N (partial last N tile)
-        uint32_t va[32];
-        float v[32];
-        tmem_ld_32x32(t_row + c0, va);
-        if (geglu) {
-          uint32_t vg[32];
-          tmem_ld_32x32(t_row + BN / 2 + c0, vg);
-          tmem_ld_wait();
+      for (int u0 = half_sel * 64; u0 < ncols_out; u0 += 128) {
+        const int ucol = col_base + u0;          // first output column of this 64-wide unit
+        if (ucol >= p.n_out) break;
+        const int uvalid = min(64, min(ncols_out - u0, p.n_out - ucol));  // columns of the unit that exist
+        // ---- stage the residual tile (coalesced 128-byte rows) ----
+        if (p.residual != nullptr && !p.out_fp32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int wa = tn * BN + c0 + j;           // weight row (a half)
-            const int wg = tn * BN + BN / 2 + c0 + j;  // weight row (gate half)
-            float a = __uint_as_float(va[j]);
-            float g = __uint_as_float(vg[j]);
-            if (p.bias != nullptr) { a += __ldg(p.bias + wa); g += __ldg(p.bias + wg); }
-            a = round_bf16(a);
-            g = round_bf16(g);
-            const float gl = round_bf16(0.5f * g * (1.0f + erff(g * 0.70710678118654752440f)));
-            v[j] = round_bf16(a * gl);
+          for (int it = 0; it < 8; ++it) {
+            const int rowi = it * 4 + rsub;
+            const long long roff = __shfl_sync(0xffffffffu, res_off, rowi);
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (((ok_mask >> rowi) & 1u) && seg * 8 < uvalid)
+              v = *reinterpret_cast<const uint4*>(p.residual + roff + ucol + seg * 8);
+            *reinterpret_cast<uint4*>(stg + rowi * kStageRowBytes + ((seg ^ (rowi & 7)) << 4)) = v;
           }
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(va[j]);
-            if (p.bias != nullptr) x += __ldg(p.bias + min(col_base + c0 + j, p.n_out - 1));
-            v[j] = x;
-          }
-          if (!p.out_fp32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j]);
-          }
-          if (p.act == CA_ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j] / (1.0f + __expf(-v[j])));
-          }
+          __syncwarp();
         }
-        if (p.out_scale != 1.0f) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j] * p.out_scale);
-        }
-        if (row_ok) {
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          const int c0 = u0 + hsel * 32;      // column offset inside the tile's output columns
+          if (hsel * 32 >= uvalid) break;
           const int col = col_base + c0;
-          const int nvalid = min(32, p.n_out - col);
-          if (p.rowvec != nullptr) {
+          const int nvalid = min(32, uvalid - hsel * 32);
+          uint32_t va[32];
+          float v[32];
+          tmem_ld_32x32(t_row + c0, va);
+          if (geglu) {
+            uint32_t vg[32];
+            tmem_ld_32x32(t_row + BN / 2 + c0, vg);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int wa = tn * BN + c0 + j;           // weight row (value half)
+              const int wg = tn * BN + BN / 2 + c0 + j;  // weight row (gate half)
+              float a = __uint_as_float(va[j]);
+              float g = __uint_as_float(vg[j]);
+              if (p.bias != nullptr) { a += __ldg(p.bias + wa); g += __ldg(p.bias + wg); }
+              a = round_bf16(a);
+              g = round_bf16(g);
+              const float gl = round_bf16(0.5f * g * (1.0f + fast_erf(g * 0.70710678118654752440f)));
+              v[j] = round_bf16(a * gl);
+            }
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(va[j]);
+              if (p.bias != nullptr) x += __ldg(p.bias + min(col + j, p.n_out - 1));
+              v[j] = x;
+            }
+            if (!p.out_fp32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j]);
+            }
+            if (p.act == CA_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = round_bf16(__fdividef(v[j], 1.0f + __expf(-v[j])));
+            }
+          }
+          if (p.out_scale != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j] * p.out_scale);
+          }
+          if (p.rowvec != nullptr && row_ok) {
             const __nv_bfloat16* rv = p.rowvec + rv_off + col;
             if (nvalid == 32) {
 #pragma unroll
@@ -248,56 +297,64 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
               for (int j = 0; j < nvalid; ++j) v[j] = round_bf16(v[j] + __bfloat162float(rv[j]));
             }
           }
-          if (p.residual != nullptr) {
-            const __nv_bfloat16* rs = p.residual + res_off + col;
-            if (nvalid == 32) {
-#pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                const uint4 u = *(reinterpret_cast<const uint4*>(rs) + j8);
-                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = __bfloat1622float2(h[e]);
-                  v[j8 * 8 + e * 2] = round_bf16(v[j8 * 8 + e * 2] + f.x);
-                  v[j8 * 8 + e * 2 + 1] = round_bf16(v[j8 * 8 + e * 2 + 1] + f.y);
-                }
+          if (p.out_fp32) {
+            // test / debug path: fp32 result, optional residual, direct stores
+            if (row_ok) {
+              float* op = reinterpret_cast<float*>(p.out) + out_off + col;
+              for (int j = 0; j < nvalid; ++j) {
+                float x = v[j];
+                if (p.residual != nullptr) x += __bfloat162float(p.residual[res_off + col + j]);
+                op[j] = x;
               }
-            } else {
-              for (int j = 0; j < nvalid; ++j) v[j] = round_bf16(v[j] + __bfloat162float(rs[j]));
+            }
+            continue;
+          }
+          if (p.residual != nullptr) {
+            // own row of the staged residual tile: 16-byte units hsel*4 .. hsel*4+3
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const uint4 u = *reinterpret_cast<const uint4*>(stg + lane * kStageRowBytes + (((hsel * 4 + j8) ^ (lane & 7)) << 4));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h[e]);
+                v[j8 * 8 + e * 2] = round_bf16(v[j8 * 8 + e * 2] + f.x);
+                v[j8 * 8 + e * 2 + 1] = round_bf16(v[j8 * 8 + e * 2 + 1] + f.y);
+              }
             }
           }
-          if (p.blend_src != nullptr) {
+          if (p.blend_src != nullptr && row_ok) {
             const __nv_bfloat16* bs = p.blend_src + res_off + col;
             for (int j = 0; j < nvalid; ++j) {
               const float xs = __bfloat162float(bs[j]);
               v[j] = round_bf16(round_bf16(alpha_s * xs) + round_bf16(alpha_t * v[j]));
             }
           }
-          if (p.out_fp32) {
-            float* op = reinterpret_cast<float*>(p.out) + out_off + col;
-            if (nvalid == 32) {
+          // result -> own staged row (same 16-byte units that were just consumed)
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4)
-                reinterpret_cast<float4*>(op)[j4] = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-            } else {
-              for (int j = 0; j < nvalid; ++j) op[j] = v[j];
-            }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + col;
-            if (nvalid == 32) {
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4 u;
+            u.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
+            u.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
+            u.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
+            u.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
+            *reinterpret_cast<uint4*>(stg + lane * kStageRowBytes + (((hsel * 4 + j8) ^ (lane & 7)) << 4)) = u;
+          }
+        }
+        if (!p.out_fp32) {
+          __syncwarp();
+          // ---- coalesced copy-out: 4 rows x 128 bytes per warp instruction ----
+          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                uint4 u;
-                u.x = pack_bf16x2(v[j8 * 8 + 0], v[j8 * 8 + 1]);
-                u.y = pack_bf16x2(v[j8 * 8 + 2], v[j8 * 8 + 3]);
-                u.z = pack_bf16x2(v[j8 * 8 + 4], v[j8 * 8 + 5]);
-                u.w = pack_bf16x2(v[j8 * 8 + 6], v[j8 * 8 + 7]);
-                reinterpret_cast<uint4*>(op)[j8] = u;
-              }
-            } else {
-              for (int j = 0; j < nvalid; ++j) op[j] = __float2bfloat16_rn(v[j]);
+          for (int it = 0; it < 8; ++it) {
+            const int rowi = it * 4 + rsub;
+            const long long ooff = __shfl_sync(0xffffffffu, out_off, rowi);
+            if (((ok_mask >> rowi) & 1u) && seg * 8 < uvalid) {
+              const uint4 u = *reinterpret_cast<const uint4*>(stg + rowi * kStageRowBytes + ((seg ^ (rowi & 7)) << 4));
+              *reinterpret_cast<uint4*>(outp + ooff + ucol + seg * 8) = u;
             }
           }
+          __syncwarp();
         }
       }
       // all TMEM reads of this accumulator stage are complete -> hand it back to the MMA warp

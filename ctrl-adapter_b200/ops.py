@@ -57,7 +57,7 @@ class _Profiler:
         """-> {family: {"launches", "ms", "flops", "bytes"}} (synchronises)."""
         torch.cuda.synchronize()
         out = {}
-        for fam, flops, nbytes, e0, e1 in self.records:
+        for fam, flops, nbytes, e0, e1, _note in self.records:
             d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
@@ -66,7 +66,27 @@ class _Profiler:
         return out
 
 
+    def launches_table(self, top: int = 60):
+        """Per-(family, shape note) aggregation sorted by time: [{"fam","note","n","ms","tflops"}]."""
+        torch.cuda.synchronize()
+        agg = {}
+        for fam, flops, nbytes, e0, e1, note in self.records:
+            d = agg.setdefault((fam, note), {"fam": fam, "note": note, "n": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["n"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        rows = sorted(agg.values(), key=lambda r: -r["ms"])[:top]
+        for r in rows:
+            r["tflops"] = round(r["flops"] / (r["ms"] * 1e9), 1) if r["ms"] > 0 and r["flops"] else None
+            r["gbs"] = round(r["bytes"] / (r["ms"] * 1e6), 1) if r["ms"] > 0 and r["bytes"] else None
+            r["ms"] = round(r["ms"], 3)
+            del r["flops"], r["bytes"]
+        return rows
+
+
 PROFILER = _Profiler()
+NOTE = [""]  # shape note of the launch being issued (set by the GEMM / attention wrappers when profiling)
 
 
 def _launch(fam: str, flops: float, nbytes: float, name: str, *args):
@@ -78,7 +98,8 @@ def _launch(fam: str, flops: float, nbytes: float, name: str, *args):
         e0.record()
         st = getattr(lib, name)(*args)
         e1.record()
-        PROFILER.records.append((fam, flops, nbytes, e0, e1))
+        PROFILER.records.append((fam, flops, nbytes, e0, e1, NOTE[0]))
+        NOTE[0] = ""
     else:
         st = getattr(lib, name)(*args)
     check(st, name)
@@ -205,6 +226,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         rvs = None
     _fill_epilogue(d, bias=bias, act=act, out_scale=out_scale, rowvec=rowvec, rowvec_strides=rvs, residual=residual,
                    blend_src=blend_src, res_strides=rs, blend_alpha=blend_alpha)
+    if PROFILER.active:
+        NOTE[0] = f"linear m{m} k{k} n{wr} act{act} res{int(residual is not None)}"
     _launch("gemm", 2.0 * m * k * wr, 2.0 * (m * k + wr * k + m * n_out), "ca_gemm", C.byref(d), _stream())
     return out
 
@@ -280,6 +303,8 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
     _fill_epilogue(d, bias=bias, act=act, out_scale=out_scale, rowvec=rowvec, rowvec_strides=rvs if rowvec is not None else None,
                    residual=residual, blend_src=blend_src,
                    res_strides=os_ if (residual is not None or blend_src is not None) else None, blend_alpha=blend_alpha)
+    if PROFILER.active:
+        NOTE[0] = f"conv{ksize} s{stride} n{n} {h}x{w_} c{c}+{c2}->{cout} box{bw}x{bh}x{bnn}"
     _launch("gemm", 2.0 * n * ho * wo * ntaps * (c + c2) * cout,
             2.0 * (n * h * w_ * (c + c2) + w_packed.numel() + n * ho * wo * cout), "ca_gemm", C.byref(d), _stream())
     return out
@@ -344,6 +369,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hea
     d.k_row_stride, d.k_batch_stride = k.stride(1), k.stride(0)
     d.v_row_stride, d.v_batch_stride = v.stride(1), v.stride(0)
     d.out_row_stride, d.out_batch_stride = out.stride(1), out.stride(0)
+    if PROFILER.active:
+        NOTE[0] = f"attn b{b} h{heads} lq{lq} lk{lk} dp{head_dim_pad}"
     _launch("attention", 4.0 * b * heads * lq * lk * head_dim_pad, 2.0 * b * (2 * lq + 2 * lk) * ctot, "ca_attention", C.byref(d), _stream())
     return out
 

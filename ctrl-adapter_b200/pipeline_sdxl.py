@@ -42,7 +42,8 @@ class SDXLControlNetAdapterLoop:
         # row[3] of step i is the scale_model_input divisor of step i+1; the first model input is scaled here
         self.table = torch.from_numpy(self.schedule.table()).to(dev)
         self.row = self.table[0].clone()
-        first_div = float((self.schedule.sigmas[0] ** 2 + 1) ** 0.5)
+        # scale_model_input divides a bf16 tensor by a 0-dim fp32 tensor -> the divisor is cast to bf16 first
+        first_div = torch.tensor(float((self.schedule.sigmas[0] ** 2 + 1) ** 0.5), device=dev).to(BF16)
         self.model_in = (self.latents.to(BF16) / first_div).to(BF16).contiguous()
         self.prompt_embeds = prompt_embeds.to(BF16).contiguous()
         self.added = dict(text_embeds=add_text_embeds.to(BF16).contiguous(),
