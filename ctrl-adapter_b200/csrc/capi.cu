@@ -4,6 +4,7 @@
 // (symbol check) on a machine without a driver.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "kernels.h"
@@ -124,6 +125,8 @@ int ca_gemm(const ca_gemm_desc* d, void* cuda_stream) {
     else bn = 256;
   }
   if (geglu && (d->w_rows % bn) != 0) return fail(CA_ERR_INVALID, "GEGLU needs w_rows %% bn == 0");
+  // CTA pairs (tcgen05 cta_group::2, M = 256 per pair) unless CA_GEMM_1CTA is set (A/B comparison / debugging)
+  static const int ncta = getenv("CA_GEMM_1CTA") ? 1 : 2;
 
   int k_per_tap = 0;
   for (int s = 0; s < d->nsrc; ++s) {
@@ -187,14 +190,16 @@ int ca_gemm(const ca_gemm_desc* d, void* cuda_stream) {
     if (ktot % 8 != 0) return fail(CA_ERR_INVALID, "weight row length must be a multiple of 8");
     cuuint64_t dims[2] = {ktot, static_cast<cuuint64_t>(d->w_rows)};
     cuuint64_t strides[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn / ncta)};  // each CTA of a pair stages half of the N tile
     int rc = make_tmap(&tw, d->w, 2, dims, strides, box);
     if (rc) return rc;
   }
-  const long long tiles = static_cast<long long>(p.ntile[0]) * p.ntile[1] * p.ntile[2] * p.ntile[3] * p.n_tiles_n;
+  const long long tiles_m = static_cast<long long>(p.ntile[0]) * p.ntile[1] * p.ntile[2] * p.ntile[3];
+  const long long tiles = ((tiles_m + ncta - 1) / ncta) * p.n_tiles_n;  // tiles per CTA group
   if (tiles <= 0) return fail(CA_ERR_INVALID, "empty problem");
-  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  CA_LAUNCH(ca::launch_gemm_conv(bn, ta[0], ta[1], tw, p, grid, stream), "gemm_conv launch");
+  const long long max_groups = num_sms() / ncta;
+  const int grid = static_cast<int>((tiles < max_groups ? tiles : max_groups) * ncta);
+  CA_LAUNCH(ca::launch_gemm_conv(bn, ncta, ta[0], ta[1], tw, p, grid, stream), "gemm_conv launch");
 }
 
 int ca_attention(const ca_attention_desc* d, void* cuda_stream) {

@@ -36,7 +36,7 @@ struct GemmParams {
   void* out;
 };
 
-cudaError_t launch_gemm_conv(int bn, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
+cudaError_t launch_gemm_conv(int bn, int ncta, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
                              const GemmParams& p, int grid, cudaStream_t stream);
 
 struct AttnParams {
