@@ -11,6 +11,8 @@
 //                running-max rescale; final 1/l normalisation and 128 B row store.
 // With head dim 64 the CTA uses 112 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's
 // softmax overlaps the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -166,69 +168,98 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint8_t* p_row = smem_p + r * 128;
     const int sw = r & 7;
 
-    for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(kTileKV, p.lk - j * kTileKV);
+    // One KV tile of the online softmax.  MASK is only instantiated for a ragged last tile, so the hot path carries
+    // no per-element predication; TMEM loads are software pipelined (chunk c+1 is in flight while chunk c is
+    // processed); the O rescale is skipped when no row of the warp raised its running max.
+    auto tile_step = [&](auto mask_tag, int j, int kv_valid) {
+      constexpr bool MASK = decltype(mask_tag)::value;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // ---- pass 1: row max ----
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tmem_s + lane_sel + c * 32, sv);
-        tmem_ld_wait();
+      uint32_t sva[16], svb[16];
+      // ---- pass 1: row max (16-column chunks, next chunk in flight while the current one is reduced) ----
+      float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      tmem_ld_32x16(tmem_s + lane_sel, sva);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = (c * 32 + i < kv_valid) ? __uint_as_float(sv[i]) : -INFINITY;
-          mx = fmaxf(mx, s);
+      for (int c = 0; c < 8; ++c) {
+        uint32_t(&cur)[16] = (c & 1) ? svb : sva;
+        uint32_t(&nxt)[16] = (c & 1) ? sva : svb;
+        if (c < 7) tmem_ld_32x16(tmem_s + lane_sel + (c + 1) * 16, nxt);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
+          float s2 = __uint_as_float(cur[i + 2]), s3 = __uint_as_float(cur[i + 3]);
+          if (MASK) {
+            if (c * 16 + i >= kv_valid) s0 = -INFINITY;
+            if (c * 16 + i + 1 >= kv_valid) s1 = -INFINITY;
+            if (c * 16 + i + 2 >= kv_valid) s2 = -INFINITY;
+            if (c * 16 + i + 3 >= kv_valid) s3 = -INFINITY;
+          }
+          mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1); mx2 = fmaxf(mx2, s2); mx3 = fmaxf(mx3, s3);
         }
+        if (c < 7) tmem_ld_wait();
       }
-      const float m_new = mx;
-      const float alpha = fast_exp2((m_run - m_new) * sl2);  // exp2(-inf) = 0 on the first tile
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const bool same = __all_sync(0xffffffffu, m_new == m_run);
+      const float alpha = same ? 1.0f : fast_exp2((m_run - m_new) * sl2);  // exp2(-inf) = 0 on the first tile
       const float mneg = -m_new * sl2;
-      // P smem of tile j-1 must have been consumed by its PV MMA, whose result we also fold in now
+      // P smem of tile j-1 must have been consumed by its PV MMA, whose result is folded in below
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
       // ---- pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P into the swizzled A tile ----
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tmem_s + lane_sel + c * 32, sv);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      float rs0 = 0.f, rs1 = 0.f;
+      tmem_ld_32x16(tmem_s + lane_sel, sva);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), sl2, mneg));
-          float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), sl2, mneg));
-          if (c * 32 + i >= kv_valid) p0 = 0.f;
-          if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
-          rowsum += p0 + p1;
+      for (int c = 0; c < 8; ++c) {
+        uint32_t(&cur)[16] = (c & 1) ? svb : sva;
+        uint32_t(&nxt)[16] = (c & 1) ? sva : svb;
+        if (c < 7) tmem_ld_32x16(tmem_s + lane_sel + (c + 1) * 16, nxt);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(cur[i]), sl2, mneg));
+          float p1 = fast_exp2(fmaf(__uint_as_float(cur[i + 1]), sl2, mneg));
+          if (MASK) {
+            if (c * 16 + i >= kv_valid) p0 = 0.f;
+            if (c * 16 + i + 1 >= kv_valid) p1 = 0.f;
+          }
+          rs0 += p0;
+          rs1 += p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
-        uint8_t* chunk = p_row + (c >> 1) * kChunkBytes;
+        uint8_t* chunk = p_row + (c >> 2) * kChunkBytes;  // 64 columns (4 chunks of 16) per swizzle tile
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 128-byte row
+        for (int u = 0; u < 2; ++u) {
+          const int unit = (c & 3) * 2 + u;  // 16-byte unit inside the 128-byte row
           *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) =
               make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
         }
+        if (c < 7) tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);
-      l_run = l_run * alpha + rowsum;
+      l_run = l_run * alpha + (rs0 + rs1);
       // ---- fold in O_part of tile j-1, then rescale to the new running max ----
       if (j > 0) {
+        tmem_ld_32x16(tmem_o + lane_sel, sva);
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t ov[32];
-          tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
-          tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) {
+          uint32_t(&cur)[16] = (c & 1) ? svb : sva;
+          uint32_t(&nxt)[16] = (c & 1) ? sva : svb;
+          if (c < 3) tmem_ld_32x16(tmem_o + lane_sel + (c + 1) * 16, nxt);
+          if (same) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(ov[i])) * alpha;
+            for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] += __uint_as_float(cur[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = (o_acc[c * 16 + i] + __uint_as_float(cur[i])) * alpha;
+          }
+          if (c < 3) tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
@@ -238,6 +269,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       m_run = m_new;
+    };
+    for (int j = 0; j < nkv; ++j) {
+      const int kv_valid = min(kTileKV, p.lk - j * kTileKV);
+      if (kv_valid == kTileKV) tile_step(std::false_type{}, j, kv_valid);
+      else tile_step(std::true_type{}, j, kv_valid);
     }
     // last PV
     mbar_wait(o_full, (nkv - 1) & 1);
@@ -247,17 +283,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_batch_stride +
                           static_cast<long long>(row) * p.out_row_stride + h * dpad + vs * 64;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t ov[32];
-      tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
+    for (int c = 0; c < 4; ++c) {
+      uint32_t ov[16];
+      tmem_ld_32x16(tmem_o + lane_sel + c * 16, ov);
       tmem_ld_wait();
       if (row < p.lq) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = (o_acc[c * 32 + u * 8 + e] + __uint_as_float(ov[u * 8 + e])) * inv_l;
-          *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = make_uint4(
+          for (int e = 0; e < 8; ++e) f[e] = (o_acc[c * 16 + u * 8 + e] + __uint_as_float(ov[u * 8 + e])) * inv_l;
+          *reinterpret_cast<uint4*>(orow + c * 16 + u * 8) = make_uint4(
               pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
       }

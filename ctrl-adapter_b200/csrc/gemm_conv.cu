@@ -300,16 +300,25 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
             tmem_ld_32x32(t_row + BN / 2 + c0, vg);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int wa = tn * BN + c0 + j;           // weight row (value half)
-              const int wg = tn * BN + BN / 2 + c0 + j;  // weight row (gate half)
-              float a = __uint_as_float(va[j]);
-              float g = __uint_as_float(vg[j]);
-              if (p.bias != nullptr) { a += __ldg(p.bias + wa); g += __ldg(p.bias + wg); }
-              a = round_bf16(a);
-              g = round_bf16(g);
-              const float gl = round_bf16(0.5f * g * (1.0f + fast_erf(g * 0.70710678118654752440f)));
-              v[j] = round_bf16(a * gl);
+            for (int j = 0; j < 32; j += 2) {
+              const int wa = tn * BN + c0 + j;           // weight rows (value half)
+              const int wg = tn * BN + BN / 2 + c0 + j;  // weight rows (gate half)
+              float a0 = __uint_as_float(va[j]), a1 = __uint_as_float(va[j + 1]);
+              float g0 = __uint_as_float(vg[j]), g1 = __uint_as_float(vg[j + 1]);
+              if (p.bias != nullptr) {
+                const float2 ba = __ldg(reinterpret_cast<const float2*>(p.bias + wa));
+                const float2 bg = __ldg(reinterpret_cast<const float2*>(p.bias + wg));
+                a0 += ba.x; a1 += ba.y; g0 += bg.x; g1 += bg.y;
+              }
+              round2_bf16(a0, a1);
+              round2_bf16(g0, g1);
+              float l0 = 0.5f * g0 * (1.0f + fast_erf(g0 * 0.70710678118654752440f));
+              float l1 = 0.5f * g1 * (1.0f + fast_erf(g1 * 0.70710678118654752440f));
+              round2_bf16(l0, l1);
+              float r0 = a0 * l0, r1 = a1 * l1;
+              round2_bf16(r0, r1);
+              v[j] = r0;
+              v[j + 1] = r1;
             }
           } else {
             tmem_ld_wait();
@@ -321,16 +330,24 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
             }
             if (!p.out_fp32) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j]);
+              for (int j = 0; j < 32; j += 2) round2_bf16(v[j], v[j + 1]);
             }
             if (p.act == CA_ACT_SILU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = round_bf16(__fdividef(v[j], 1.0f + __expf(-v[j])));
+              for (int j = 0; j < 32; j += 2) {
+                v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+                v[j + 1] = __fdividef(v[j + 1], 1.0f + __expf(-v[j + 1]));
+                round2_bf16(v[j], v[j + 1]);
+              }
             }
           }
           if (p.out_scale != 1.0f) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = round_bf16(v[j] * p.out_scale);
+            for (int j = 0; j < 32; j += 2) {
+              v[j] *= p.out_scale;
+              v[j + 1] *= p.out_scale;
+              round2_bf16(v[j], v[j + 1]);
+            }
           }
           if (p.rowvec != nullptr && row_ok) {
             const __nv_bfloat16* rv = p.rowvec + rv_off + col;
@@ -342,8 +359,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float2 f = __bfloat1622float2(h[e]);
-                  v[j8 * 8 + e * 2] = round_bf16(v[j8 * 8 + e * 2] + f.x);
-                  v[j8 * 8 + e * 2 + 1] = round_bf16(v[j8 * 8 + e * 2 + 1] + f.y);
+                  v[j8 * 8 + e * 2] += f.x;
+                  v[j8 * 8 + e * 2 + 1] += f.y;
+                  round2_bf16(v[j8 * 8 + e * 2], v[j8 * 8 + e * 2 + 1]);
                 }
               }
             } else {
@@ -376,8 +394,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float2 f = __bfloat1622float2(h[e]);
-                v[j8 * 8 + e * 2] = round_bf16(v[j8 * 8 + e * 2] + f.x);
-                v[j8 * 8 + e * 2 + 1] = round_bf16(v[j8 * 8 + e * 2 + 1] + f.y);
+                v[j8 * 8 + e * 2] += f.x;
+                v[j8 * 8 + e * 2 + 1] += f.y;
+                round2_bf16(v[j8 * 8 + e * 2], v[j8 * 8 + e * 2 + 1]);
               }
             }
           }
