@@ -59,6 +59,7 @@ class AttentionDesc(C.Structure):
         ("k_row_stride", C.c_int64), ("k_batch_stride", C.c_int64),
         ("v_row_stride", C.c_int64), ("v_batch_stride", C.c_int64),
         ("out_row_stride", C.c_int64), ("out_batch_stride", C.c_int64),
+        ("kv_batch_div", C.c_int32),
     ]
 
 
@@ -83,7 +84,8 @@ SIGNATURES = {
     "ca_router_weights": [_P, _P, _I, _I, _P, _P],
     "ca_router_merge": [_P, _P, _I, _L, _P, _P],
     "ca_cfg_euler": [_P, _P, _P, _L, _F, _P, _I, _P, _P, _P],
-    "ca_cfg_ddim": [_P, _P, _P, _L, _F, _P, _I, _P, _P, _P],
+    "ca_cfg_ddim": [_P, _P, _P, _L, _F, _P, _I, _I, _P, _P, _P],
+    "ca_i2vgen_latent_encoder": [_P, _I, _I, _L, _I, _P, _P, _P],
     "ca_temporal_attention": [_P, _P, _P, _I, _I, _L, _I, _F, _L, _P, _P],
 }
 _RESTYPES = {"ca_last_error": C.c_char_p}

@@ -426,5 +426,5 @@ def router_merge(res_lists, weights_row: torch.Tensor, active: List[int], num_fr
     """Weighted merge of E ControlNet outputs for one block (i2vgen_xl pipeline :1001-1022).
     Reproduces the reference indexing quirk Q6: ``w.repeat_interleave(F)[e]`` == ``w[e // F]``."""
     w_rep = weights_row.repeat_interleave(num_frames)
-    sel = torch.stack([w_rep[e] for e in active]).float().contiguous()
+    sel = w_rep[torch.tensor(active, device=weights_row.device)].float().contiguous()
     return ops.router_merge([to_channels_last_bf16(res_lists[e]) for e in active], sel)

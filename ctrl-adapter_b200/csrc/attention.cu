@@ -109,8 +109,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_arrive_expect_tx(&kv_full[st], Cfg::kStageBytes);
         uint8_t* dst = smem_kv + st * Cfg::kStageBytes;
         for (int c = 0; c < DQ; ++c)
-          tma_load_3d(dst + c * kChunkBytes, &tmap_k, &kv_full[st], h * dpad + c * 64, j * kTileKV, b);
-        tma_load_3d(dst + DQ * kChunkBytes, &tmap_v, &kv_full[st], h * dpad + vs * 64, j * kTileKV, b);
+          tma_load_3d(dst + c * kChunkBytes, &tmap_k, &kv_full[st], h * dpad + c * 64, j * kTileKV, b / p.kv_batch_div);
+        tma_load_3d(dst + DQ * kChunkBytes, &tmap_v, &kv_full[st], h * dpad + vs * 64, j * kTileKV, b / p.kv_batch_div);
       }
     }
   } else if (warp == 1) {

@@ -208,6 +208,8 @@ int ca_attention(const ca_attention_desc* d, void* cuda_stream) {
   if (d->head_dim_pad != 64 && d->head_dim_pad != 128 && d->head_dim_pad != 192)
     return fail(CA_ERR_UNSUPPORTED, "head_dim_pad must be 64, 128 or 192 (got %d)", d->head_dim_pad);
   if (d->batch < 1 || d->heads < 1 || d->lq < 1 || d->lk < 1) return fail(CA_ERR_INVALID, "empty attention problem");
+  const int kv_div = d->kv_batch_div > 0 ? d->kv_batch_div : 1;
+  if (d->batch % kv_div != 0) return fail(CA_ERR_INVALID, "batch must be a multiple of kv_batch_div");
   const cuuint64_t ctot = static_cast<cuuint64_t>(d->heads) * d->head_dim_pad;
   CUtensorMap tq, tk, tv;
   const cuuint32_t box[3] = {64, 128, 1};
@@ -218,7 +220,7 @@ int ca_attention(const ca_attention_desc* d, void* cuda_stream) {
     if (rc) return rc;
   }
   {
-    cuuint64_t dims[3] = {ctot, (cuuint64_t)d->lk, (cuuint64_t)d->batch};
+    cuuint64_t dims[3] = {ctot, (cuuint64_t)d->lk, (cuuint64_t)(d->batch / kv_div)};
     cuuint64_t st[2] = {(cuuint64_t)d->k_row_stride * 2, (cuuint64_t)d->k_batch_stride * 2};
     int rc = make_tmap(&tk, d->k, 3, dims, st, box);
     if (rc) return rc;
@@ -228,6 +230,7 @@ int ca_attention(const ca_attention_desc* d, void* cuda_stream) {
   }
   ca::AttnParams p;
   p.batch = d->batch; p.heads = d->heads; p.lq = d->lq; p.lk = d->lk;
+  p.kv_batch_div = kv_div;
   p.dqk_chunks = d->head_dim_pad / 64;
   p.v_slices = d->head_dim_pad / 64;
   p.scale_log2 = d->scale * 1.4426950408889634f;
@@ -296,9 +299,15 @@ int ca_cfg_euler(const void* eu, const void* et, const float* lat, int64_t n, fl
                                  round_latents_bf16, lat_out, (__nv_bfloat16*)next_in, (cudaStream_t)s), "cfg_euler");
 }
 int ca_cfg_ddim(const void* eu, const void* et, const float* lat, int64_t n, float g, const float* step_row,
-                int32_t round_latents_bf16, float* lat_out, void* next_in, void* s) {
+                int32_t round_latents_bf16, int32_t v_prediction, float* lat_out, void* next_in, void* s) {
   CA_LAUNCH(ca::launch_cfg_ddim((const __nv_bfloat16*)eu, (const __nv_bfloat16*)et, lat, n, g, step_row,
-                                round_latents_bf16, lat_out, (__nv_bfloat16*)next_in, (cudaStream_t)s), "cfg_ddim");
+                                round_latents_bf16, v_prediction, lat_out, (__nv_bfloat16*)next_in, (cudaStream_t)s),
+            "cfg_ddim");
+}
+int ca_i2vgen_latent_encoder(const void* x, int32_t clips, int32_t frames, int64_t hw, int32_t c_stride,
+                             const float* params, void* y, void* s) {
+  CA_LAUNCH(ca::launch_i2vgen_latent_encoder((const __nv_bfloat16*)x, clips, frames, hw, c_stride, params,
+                                             (__nv_bfloat16*)y, (cudaStream_t)s), "i2vgen_latent_encoder");
 }
 int ca_temporal_attention(const void* q, const void* k, const void* v, int32_t clips, int32_t frames, int64_t hw,
                           int32_t heads, float scale, int64_t in_row_stride, void* out, void* s) {

@@ -294,29 +294,137 @@ cudaError_t launch_cfg_euler(const __nv_bfloat16* eps_uncond, const __nv_bfloat1
                                                            round_latents_bf16, latents_out, model_in_next);
   return cudaGetLastError();
 }
-// DDIM (eta 0, epsilon prediction): row = {t, alpha_prod_t, alpha_prod_prev, -}
+// DDIM (eta 0): row = {t, alpha_prod_t, alpha_prod_prev, -}; epsilon- or v-prediction model output
 __global__ void cfg_ddim_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
                                 const float* __restrict__ lat, long long n, float g, const float* __restrict__ row,
-                                int round_lat, float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
+                                int round_lat, int vpred, float* __restrict__ lat_out,
+                                __nv_bfloat16* __restrict__ next_in) {
   const float a_t = row[1], a_prev = row[2];
-  const float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), sap = sqrtf(a_prev), sbp = sqrtf(1.f - a_prev);
+  float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), sap = sqrtf(a_prev), sbp = sqrtf(1.f - a_prev);
+  if (round_lat) {
+    // diffusers' DDIMScheduler.step does not up-cast: with bf16 latents every product / sum below is a bf16 op and the
+    // 0-dim fp32 coefficients are cast to bf16 by type promotion before they are used
+    sa = round_bf16(sa); sb = round_bf16(sb); sap = round_bf16(sap); sbp = round_bf16(sbp);
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float u = __bfloat162float(eu[i]), c = __bfloat162float(et[i]);
-    const float eps = round_bf16(u + round_bf16(g * round_bf16(c - u)));
+    const float mo = round_bf16(u + round_bf16(g * round_bf16(c - u)));  // guided model output
     const float x = lat[i];
-    const float x0 = (x - sb * eps) / sa;
-    float xn = sap * x0 + sbp * eps;
-    if (round_lat) xn = round_bf16(xn);
+    float x0, eps, xn;
+    if (round_lat) {
+      if (vpred) {
+        x0 = round_bf16(round_bf16(sa * x) - round_bf16(sb * mo));
+        eps = round_bf16(round_bf16(sa * mo) + round_bf16(sb * x));
+      } else {
+        x0 = round_bf16(round_bf16(x - round_bf16(sb * mo)) / sa);
+        eps = mo;
+      }
+      xn = round_bf16(round_bf16(sap * x0) + round_bf16(sbp * eps));
+    } else {
+      if (vpred) {
+        x0 = sa * x - sb * mo;
+        eps = sa * mo + sb * x;
+      } else {
+        x0 = (x - sb * mo) / sa;
+        eps = mo;
+      }
+      xn = sap * x0 + sbp * eps;
+    }
     lat_out[i] = xn;
     if (next_in) next_in[i] = __float2bfloat16_rn(xn);
   }
 }
 cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
                             long long n, float guidance, const float* step_row, int round_latents_bf16,
-                            float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream) {
+                            int v_prediction, float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream) {
   cfg_ddim_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, step_row,
-                                                          round_latents_bf16, latents_out, model_in_next);
+                                                          round_latents_bf16, v_prediction, latents_out, model_in_next);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// I2VGen-XL image-latent temporal encoder: one thread per (clip, pixel); sequence = F frames x 4 channels.
+// LN(4) -> 2-head attention (head dim 4) -> +x -> FF (4 -> 16 GELU -> 4) -> +h.  bf16 rounding after each
+// Linear / attention output as on the autocast path.  Tiny and step-invariant (run once per generation).
+// ---------------------------------------------------------------------------------------------
+__global__ void i2vgen_latent_encoder_kernel(const __nv_bfloat16* __restrict__ x, int frames, long long hw,
+                                             int c_stride, const float* __restrict__ prm, long long total,
+                                             __nv_bfloat16* __restrict__ y) {
+  __shared__ float sp[288];
+  for (int i = threadIdx.x; i < 288; i += blockDim.x) sp[i] = prm[i];
+  __syncthreads();
+  const float* ln_w = sp; const float* ln_b = sp + 4; const float* wq = sp + 8; const float* wk = sp + 40;
+  const float* wv = sp + 72; const float* wo = sp + 104; const float* bo = sp + 136; const float* w1 = sp + 140;
+  const float* b1 = sp + 204; const float* w2 = sp + 220;
+  // layout: ln_w[4] ln_b[4] wq[32] wk[32] wv[32] wo[32] bo[4] w1[64] b1[16] w2[64] b2[4]  (total 288)
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const long long pix = idx % hw, clip = idx / hw;
+  const long long fstride = hw * c_stride;
+  const __nv_bfloat16* xb = x + (clip * frames * hw + pix) * c_stride;
+  __nv_bfloat16* yb = y + (clip * frames * hw + pix) * c_stride;
+  float xin[32][4], q[32][8], k[32][8], v[32][8];
+  for (int f = 0; f < frames; ++f) {
+    float m = 0.f;
+    for (int c = 0; c < 4; ++c) { xin[f][c] = __bfloat162float(xb[f * fstride + c]); m += xin[f][c]; }
+    m *= 0.25f;
+    float var = 0.f;
+    for (int c = 0; c < 4; ++c) { const float d = xin[f][c] - m; var += d * d; }
+    const float rstd = rsqrtf(var * 0.25f + 1e-5f);
+    float n4[4];
+    for (int c = 0; c < 4; ++c) n4[c] = round_bf16((xin[f][c] - m) * rstd * ln_w[c] + ln_b[c]);
+    for (int o = 0; o < 8; ++o) {
+      float aq = 0.f, ak = 0.f, av = 0.f;
+      for (int c = 0; c < 4; ++c) { aq += wq[o * 4 + c] * n4[c]; ak += wk[o * 4 + c] * n4[c]; av += wv[o * 4 + c] * n4[c]; }
+      q[f][o] = round_bf16(aq); k[f][o] = round_bf16(ak); v[f][o] = round_bf16(av);
+    }
+  }
+  for (int f = 0; f < frames; ++f) {
+    float att[8];
+    for (int hd = 0; hd < 2; ++hd) {
+      float s[32], mx = -INFINITY;
+      for (int g2 = 0; g2 < frames; ++g2) {
+        float d = 0.f;
+        for (int e = 0; e < 4; ++e) d += q[f][hd * 4 + e] * k[g2][hd * 4 + e];
+        s[g2] = d * 0.5f;  // head dim 4 -> scale 4^-0.5
+        mx = fmaxf(mx, s[g2]);
+      }
+      float l = 0.f, o4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int g2 = 0; g2 < frames; ++g2) {
+        const float pe = __expf(s[g2] - mx);
+        l += pe;
+        for (int e = 0; e < 4; ++e) o4[e] += pe * v[g2][hd * 4 + e];
+      }
+      for (int e = 0; e < 4; ++e) att[hd * 4 + e] = round_bf16(o4[e] / l);
+    }
+    float h4[4];
+    for (int c = 0; c < 4; ++c) {
+      float a = bo[c];
+      for (int o = 0; o < 8; ++o) a += wo[c * 8 + o] * att[o];
+      h4[c] = round_bf16(round_bf16(a) + xin[f][c]);
+    }
+    float u16[16];
+    for (int j = 0; j < 16; ++j) {
+      float a = b1[j];
+      for (int c = 0; c < 4; ++c) a += w1[j * 4 + c] * h4[c];
+      a = round_bf16(a);
+      u16[j] = round_bf16(0.5f * a * (1.0f + erff(a * 0.70710678118654752440f)));
+    }
+    const float* b2p = sp + 284;
+    for (int c = 0; c < 4; ++c) {
+      float a = b2p[c];
+      for (int j = 0; j < 16; ++j) a += w2[c * 16 + j] * u16[j];
+      yb[f * fstride + c] = __float2bfloat16_rn(round_bf16(a) + h4[c]);
+    }
+  }
+}
+cudaError_t launch_i2vgen_latent_encoder(const __nv_bfloat16* x, int clips, int frames, long long hw, int c_stride,
+                                         const float* params, __nv_bfloat16* y, cudaStream_t stream) {
+  if (frames > 32 || frames < 1) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(clips) * hw;
+  i2vgen_latent_encoder_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, 0, stream>>>(x, frames, hw, c_stride,
+                                                                                          params, total, y);
   return cudaGetLastError();
 }
 

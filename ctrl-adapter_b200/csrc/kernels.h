@@ -41,6 +41,7 @@ cudaError_t launch_gemm_conv(int bn, int ncta, const CUtensorMap& a0, const CUte
 
 struct AttnParams {
   int batch, heads, lq, lk;
+  int kv_batch_div;    // K/V batch index = query batch index / kv_batch_div (context shared by the frames of a clip)
   int dqk_chunks;      // padded head dim / 64 used for QK^T
   int v_slices;        // padded head dim / 64 (PV is computed one 64-wide slice per CTA)
   float scale_log2;    // softmax scale * log2(e)
@@ -83,7 +84,9 @@ cudaError_t launch_cfg_euler(const __nv_bfloat16* eps_uncond, const __nv_bfloat1
                              float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream);
 cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
                             long long n, float guidance, const float* step_row, int round_latents_bf16,
-                            float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream);
+                            int v_prediction, float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream);
+cudaError_t launch_i2vgen_latent_encoder(const __nv_bfloat16* x, int clips, int frames, long long hw, int c_stride,
+                                         const float* params, __nv_bfloat16* y, cudaStream_t stream);
 cudaError_t launch_temporal_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v,
                                       int clips, int frames, long long hw, int heads, float scale,
                                       long long in_row_stride, __nv_bfloat16* out, cudaStream_t stream);

@@ -184,7 +184,7 @@ class Attention(Packable):
             pk["wqkv"] = _bf(torch.cat([wq, wk, wv], 0))
         return pk
 
-    def forward(self, x, ctx=None, residual=None, kv=None):
+    def forward(self, x, ctx=None, residual=None, kv=None, kv_batch_div: int = 1):
         """x [B, L, D] (normalised tokens); ctx [B, Lk, Dc]; returns to_out(attn) + residual, shape [B, L, D]."""
         pk = self.packed()
         b, l, dq = x.shape
@@ -198,7 +198,7 @@ class Attention(Packable):
         else:
             qkv = ops.linear(x.reshape(b * l, dq), pk["wqkv"]).reshape(b, l, 3 * inner)
             q, k, v = qkv[:, :, :inner], qkv[:, :, inner:2 * inner], qkv[:, :, 2 * inner:]
-        o = ops.attention(q, k, v, self.heads, dp, self.dim_head ** -0.5)
+        o = ops.attention(q, k, v, self.heads, dp, self.dim_head ** -0.5, kv_batch_div=kv_batch_div if self.is_cross else 1)
         out = ops.linear(o.reshape(b * l, inner), pk["wo"], pk["bo"],
                          residual=None if residual is None else residual.reshape(b * l, dq))
         return out.reshape(b, l, dq)
@@ -251,10 +251,10 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = Norm(dim, 1e-5)
         self.ff = FeedForward(dim)
 
-    def forward(self, h, ctx, ff_kw=None):
+    def forward(self, h, ctx, ff_kw=None, kv_batch_div: int = 1):
         b, l, d = h.shape
         h = self.attn1(self.norm1.layer_norm(h), residual=h)
-        h = self.attn2(self.norm2.layer_norm(h), ctx=ctx, residual=h)
+        h = self.attn2(self.norm2.layer_norm(h), ctx=ctx, residual=h, kv_batch_div=kv_batch_div)
         out = self.ff(self.norm3.layer_norm(h).reshape(b * l, d), residual=h.reshape(b * l, d), **(ff_kw or {}))
         return out.reshape(b, l, d)
 
@@ -310,13 +310,13 @@ class Transformer2DModel(nn.Module):
         w, b = m.packed()
         return w, b
 
-    def forward(self, x, ctx):
+    def forward(self, x, ctx, kv_batch_div: int = 1):
         n, hh, ww, c = x.shape
         t = self.norm.group_norm(x, silu=False).reshape(n * hh * ww, c)
         w, b = self._w(self.proj_in)
         h = ops.linear(t, w, b).reshape(n, hh * ww, -1)
         for blk in self.transformer_blocks:
-            h = blk(h, ctx)
+            h = blk(h, ctx, kv_batch_div=kv_batch_div)
         w, b = self._w(self.proj_out)
         out = ops.linear(h.reshape(n * hh * ww, -1), w, b, residual=x.reshape(n * hh * ww, c))
         return out.reshape(n, hh, ww, c)

@@ -353,8 +353,9 @@ def temporal_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.
 # attention
 # ----------------------------------------------------------------------------------------------
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, head_dim_pad: int, scale: float,
-              out: Optional[torch.Tensor] = None):
-    """q [B, Lq, heads*Dp], k/v [B, Lk, heads*Dp] (last dim contiguous, row/batch strided views allowed)."""
+              out: Optional[torch.Tensor] = None, kv_batch_div: int = 1):
+    """q [B, Lq, heads*Dp], k/v [B / kv_batch_div, Lk, heads*Dp] (last dim contiguous, row/batch strided views
+    allowed).  kv_batch_div > 1: consecutive query batches (the frames of a clip) share one K/V context."""
     b, lq, ctot = q.shape
     lk = k.shape[1]
     assert ctot == heads * head_dim_pad and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
@@ -369,6 +370,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hea
     d.k_row_stride, d.k_batch_stride = k.stride(1), k.stride(0)
     d.v_row_stride, d.v_batch_stride = v.stride(1), v.stride(0)
     d.out_row_stride, d.out_batch_stride = out.stride(1), out.stride(0)
+    d.kv_batch_div = kv_batch_div
     if PROFILER.active:
         NOTE[0] = f"attn b{b} h{heads} lq{lq} lk{lk} dp{head_dim_pad}"
     _launch("attention", 4.0 * b * heads * lq * lk * head_dim_pad, 2.0 * b * (2 * lq + 2 * lk) * ctot, "ca_attention", C.byref(d), _stream())
@@ -537,12 +539,22 @@ def cfg_euler(eps_uncond, eps_text, latents, guidance, step_row, latents_out=Non
 
 
 def cfg_ddim(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None, model_in_next=None,
-             round_latents_bf16: bool = True):
+             round_latents_bf16: bool = True, v_prediction: bool = False):
     """step_row: device fp32 [4] = (t, alpha_prod_t, alpha_prod_prev, -)."""
     _req(eps_uncond); _req(eps_text); _req(latents, torch.float32); _req(step_row, torch.float32)
     if latents_out is None:
         latents_out = torch.empty_like(latents)
     _launch("cfg_ddim", 0.0, 0.0, "ca_cfg_ddim", eps_uncond.data_ptr(), eps_text.data_ptr(), latents.data_ptr(), latents.numel(),
-                                  float(guidance), step_row.data_ptr(), int(round_latents_bf16),
+                                  float(guidance), step_row.data_ptr(), int(round_latents_bf16), int(v_prediction),
                                   latents_out.data_ptr(), _ptr(model_in_next), _stream())
     return latents_out
+
+
+def i2vgen_latent_encoder(x: torch.Tensor, clips: int, frames: int, params: torch.Tensor):
+    """x [clips*frames, H, W, Cs] bf16 (first 4 channels used); params fp32 [288] (layout: include/ctrl_adapter_b200.h)."""
+    _req(x); _req(params, torch.float32)
+    bf, h, w_, cs = x.shape
+    y = torch.zeros_like(x)
+    _launch("i2vgen_latent_encoder", 0.0, 4.0 * x.numel(), "ca_i2vgen_latent_encoder", x.data_ptr(), clips, frames,
+            h * w_, cs, params.data_ptr(), y.data_ptr(), _stream())
+    return y

@@ -47,22 +47,52 @@ class EulerDiscreteSchedule:
         return rows
 
 
+def _betas_squaredcos_cap_v2(n: int, max_beta: float = 0.999):
+    import math
+    bar = lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2  # noqa: E731
+    return np.array([min(1 - bar((i + 1) / n) / bar(i / n), max_beta) for i in range(n)], dtype=np.float32)
+
+
+def _rescale_zero_terminal_snr(betas: np.ndarray) -> np.ndarray:
+    alphas = 1.0 - betas
+    ac = np.cumprod(alphas, axis=0)
+    s = np.sqrt(ac)
+    s0, sT = s[0].copy(), s[-1].copy()
+    s = (s - sT) * (s0 / (s0 - sT))
+    ac = s ** 2
+    alphas = np.concatenate([ac[0:1], ac[1:] / ac[:-1]])
+    return (1.0 - alphas).astype(np.float32)
+
+
 class DDIMSchedule:
-    """DDIM, eta = 0, epsilon prediction, "leading" spacing, steps_offset 1, no sample clipping."""
+    """DDIM, eta = 0, "leading" spacing, steps_offset 1, no sample clipping.  Defaults = the I2VGen-XL scheduler
+    (ali-vilab/i2vgen-xl scheduler_config.json, restated from memory -- the file is not part of the reference repo):
+    squaredcos_cap_v2 betas, rescale_betas_zero_snr, v_prediction, set_alpha_to_one."""
 
     def __init__(self, num_inference_steps: int, num_train_timesteps: int = 1000, steps_offset: int = 1,
-                 beta_schedule: str = "scaled_linear", set_alpha_to_one: bool = False):
-        self.ac = _alphas_cumprod(n=num_train_timesteps, schedule=beta_schedule)
+                 beta_schedule: str = "squaredcos_cap_v2", rescale_betas_zero_snr: bool = True,
+                 set_alpha_to_one: bool = True, prediction_type: str = "v_prediction"):
+        if beta_schedule == "squaredcos_cap_v2":
+            betas = _betas_squaredcos_cap_v2(num_train_timesteps)
+        elif beta_schedule == "scaled_linear":
+            betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, num_train_timesteps, dtype=np.float32) ** 2
+        else:
+            raise ValueError(beta_schedule)
+        if rescale_betas_zero_snr:
+            betas = _rescale_zero_terminal_snr(betas)
+        self.ac = np.cumprod(1.0 - betas, axis=0).astype(np.float32)
         step_ratio = num_train_timesteps // num_inference_steps
         self.timesteps = ((np.arange(0, num_inference_steps) * step_ratio).round()[::-1].copy().astype(np.int64)
                           + steps_offset)
         self.step_ratio = step_ratio
         self.final_alpha = 1.0 if set_alpha_to_one else float(self.ac[0])
         self.init_noise_sigma = 1.0
+        self.v_prediction = prediction_type == "v_prediction"
 
     def table(self):
+        """[steps, 4] fp32 rows (t, alpha_prod_t, alpha_prod_prev, 0) consumed by ca_cfg_ddim."""
         rows = np.zeros((len(self.timesteps), 4), dtype=np.float32)
         for i, t in enumerate(self.timesteps):
             prev = t - self.step_ratio
-            rows[i] = (t, self.ac[t], self.ac[prev] if prev >= 0 else self.final_alpha, 1.0)
+            rows[i] = (t, self.ac[t], self.ac[prev] if prev >= 0 else self.final_alpha, 0.0)
         return rows

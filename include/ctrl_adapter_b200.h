@@ -110,6 +110,8 @@ typedef struct ca_attention_desc {
   int64_t k_row_stride, k_batch_stride;
   int64_t v_row_stride, v_batch_stride;
   int64_t out_row_stride, out_batch_stride;
+  int32_t kv_batch_div;                 /* K/V batch = query batch / kv_batch_div (>= 1): one context shared by the
+                                           frames of a clip (I2VGen-XL `context_emb.repeat_interleave(num_frames)`) */
 } ca_attention_desc;
 int ca_attention(const ca_attention_desc* d, void* cuda_stream);
 
@@ -178,8 +180,15 @@ int ca_cfg_euler(const void* eps_uncond, const void* eps_text, const float* late
                  const float* step_row, int32_t round_latents_bf16, float* latents_out, void* model_in_next,
                  void* cuda_stream);
 int ca_cfg_ddim(const void* eps_uncond, const void* eps_text, const float* latents_in, int64_t n, float guidance,
-                const float* step_row, int32_t round_latents_bf16, float* latents_out, void* model_in_next,
-                void* cuda_stream);
+                const float* step_row, int32_t round_latents_bf16, int32_t v_prediction, float* latents_out,
+                void* model_in_next, void* cuda_stream);
+
+/* I2VGen-XL image-latent temporal encoder (unet_i2vgen_xl.py:51-101, called at :648): per pixel, over the F frames of a
+ * clip, on 4 channels: h = x + to_out(attn(LN(x))) (2 heads x 4); y = h + W2 gelu(W1 h).  Step-invariant conditioning,
+ * computed once per generation.  x/y: [clips*frames, hw, c_stride] bf16 (first 4 channels used).  params: fp32 device
+ * array {ln_w[4], ln_b[4], wq[8*4], wk[8*4], wv[8*4], wo[4*8], bo[4], w1[16*4], b1[16], w2[4*16], b2[4]}. */
+int ca_i2vgen_latent_encoder(const void* x, int32_t clips, int32_t frames, int64_t hw, int32_t c_stride,
+                             const float* params, void* y, void* cuda_stream);
 
 /*
  * Temporal self-attention over the frame axis (diffusers TemporalBasicTransformerBlock.attn1 reached from

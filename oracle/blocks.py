@@ -130,13 +130,25 @@ class FeedForward(nn.Module):
         if inner_dim is None:
             inner_dim = int(dim * mult)
         dim_out = dim_out if dim_out is not None else dim
-        assert activation_fn == "geglu"
-        self.net = nn.ModuleList([GEGLU(dim, inner_dim, bias=bias), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out, bias=bias)])
+        assert activation_fn in ("geglu", "gelu")
+        act = GEGLU(dim, inner_dim, bias=bias) if activation_fn == "geglu" else _GELUProj(dim, inner_dim, bias=bias)
+        self.net = nn.ModuleList([act, nn.Dropout(dropout), nn.Linear(inner_dim, dim_out, bias=bias)])
 
     def forward(self, hidden_states):
         for m in self.net:
             hidden_states = m(hidden_states)
         return hidden_states
+
+
+class _GELUProj(nn.Module):
+    """diffusers activations.GELU (approximate="none"): Linear followed by exact erf GELU."""
+
+    def __init__(self, dim_in: int, dim_out: int, bias: bool = True):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out, bias=bias)
+
+    def forward(self, hidden_states):
+        return F.gelu(self.proj(hidden_states))
 
 
 class BasicTransformerBlock(nn.Module):
@@ -718,4 +730,343 @@ def get_up_block(up_block_type: str, num_layers: int, in_channels: int, out_chan
                                   cross_attention_dim=cross_attention_dim, num_attention_heads=num_attention_heads,
                                   use_linear_projection=use_linear_projection, only_cross_attention=only_cross_attention,
                                   upcast_attention=upcast_attention)
+    raise ValueError(f"{up_block_type} does not exist.")
+
+
+# ------------------------------------------------------------------------------------------------
+# 3-D (video) blocks of diffusers v0.27.2 used by I2VGenXLUNet
+# (reference: /root/reference/i2vgen_xl/models/unets/unet_i2vgen_xl.py:30-38 imports them from
+#  diffusers.models.unets.unet_3d_blocks / transformers.transformer_temporal / resnet)
+# ------------------------------------------------------------------------------------------------
+class GELUProj(nn.Module):
+    """diffusers activations.GELU: Linear followed by exact (erf) GELU."""
+
+    def __init__(self, dim_in: int, dim_out: int, bias: bool = True):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out, bias=bias)
+
+    def forward(self, hidden_states):
+        return F.gelu(self.proj(hidden_states))
+
+
+class FeedForwardGELU(nn.Module):
+    """FeedForward(activation_fn="gelu", inner_dim=...) as used by I2VGenXLTransformerTemporalEncoder."""
+
+    def __init__(self, dim: int, inner_dim: int, dim_out: Optional[int] = None, bias: bool = True):
+        super().__init__()
+        dim_out = dim_out if dim_out is not None else dim
+        self.net = nn.ModuleList([GELUProj(dim, inner_dim, bias=bias), nn.Dropout(0.0), nn.Linear(inner_dim, dim_out, bias=bias)])
+
+    def forward(self, hidden_states):
+        for m in self.net:
+            hidden_states = m(hidden_states)
+        return hidden_states
+
+
+class TemporalConvLayer(nn.Module):
+    """4 x (GroupNorm -> SiLU -> [Dropout] -> Conv3d (3,1,1)) with identity skip; last conv zero-initialised."""
+
+    def __init__(self, in_dim: int, out_dim: Optional[int] = None, dropout: float = 0.0, norm_num_groups: int = 32):
+        super().__init__()
+        out_dim = out_dim or in_dim
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.conv1 = nn.Sequential(nn.GroupNorm(norm_num_groups, in_dim), nn.SiLU(),
+                                   nn.Conv3d(in_dim, out_dim, (3, 1, 1), padding=(1, 0, 0)))
+        self.conv2 = nn.Sequential(nn.GroupNorm(norm_num_groups, out_dim), nn.SiLU(), nn.Dropout(dropout),
+                                   nn.Conv3d(out_dim, in_dim, (3, 1, 1), padding=(1, 0, 0)))
+        self.conv3 = nn.Sequential(nn.GroupNorm(norm_num_groups, out_dim), nn.SiLU(), nn.Dropout(dropout),
+                                   nn.Conv3d(out_dim, in_dim, (3, 1, 1), padding=(1, 0, 0)))
+        self.conv4 = nn.Sequential(nn.GroupNorm(norm_num_groups, out_dim), nn.SiLU(), nn.Dropout(dropout),
+                                   nn.Conv3d(out_dim, in_dim, (3, 1, 1), padding=(1, 0, 0)))
+        nn.init.zeros_(self.conv4[-1].weight)
+        nn.init.zeros_(self.conv4[-1].bias)
+
+    def forward(self, hidden_states, num_frames: int = 1):
+        hidden_states = hidden_states[None, :].reshape((-1, num_frames) + hidden_states.shape[1:]).permute(0, 2, 1, 3, 4)
+        identity = hidden_states
+        hidden_states = self.conv1(hidden_states)
+        hidden_states = self.conv2(hidden_states)
+        hidden_states = self.conv3(hidden_states)
+        hidden_states = self.conv4(hidden_states)
+        hidden_states = identity + hidden_states
+        hidden_states = hidden_states.permute(0, 2, 1, 3, 4).reshape(
+            (hidden_states.shape[0] * hidden_states.shape[2], -1) + hidden_states.shape[3:])
+        return hidden_states
+
+
+class TransformerTemporalModel(nn.Module):
+    """Frame-axis transformer: GroupNorm (5-D statistics) -> proj_in -> BasicTransformerBlock(double self-attention)
+    over (batch*h*w, frames, c) -> proj_out -> + residual."""
+
+    def __init__(self, num_attention_heads: int = 16, attention_head_dim: int = 88, in_channels: Optional[int] = None,
+                 out_channels: Optional[int] = None, num_layers: int = 1, dropout: float = 0.0, norm_num_groups: int = 32,
+                 cross_attention_dim: Optional[int] = None, attention_bias: bool = False,
+                 double_self_attention: bool = True, **_unused):
+        super().__init__()
+        inner_dim = num_attention_heads * attention_head_dim
+        self.in_channels = in_channels
+        self.norm = nn.GroupNorm(num_groups=norm_num_groups, num_channels=in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner_dim)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(inner_dim, num_attention_heads, attention_head_dim, dropout=dropout,
+                                  cross_attention_dim=cross_attention_dim, attention_bias=attention_bias,
+                                  double_self_attention=double_self_attention) for _ in range(num_layers)])
+        self.proj_out = nn.Linear(inner_dim, in_channels)
+
+    def forward(self, hidden_states, encoder_hidden_states=None, num_frames: int = 1, **_kw):
+        batch_frames, channel, height, width = hidden_states.shape
+        batch_size = batch_frames // num_frames
+        residual = hidden_states
+        hidden_states = hidden_states[None, :].reshape(batch_size, num_frames, channel, height, width)
+        hidden_states = hidden_states.permute(0, 2, 1, 3, 4)
+        hidden_states = self.norm(hidden_states)
+        hidden_states = hidden_states.permute(0, 3, 4, 2, 1).reshape(batch_size * height * width, num_frames, channel)
+        hidden_states = self.proj_in(hidden_states)
+        for block in self.transformer_blocks:
+            hidden_states = block(hidden_states, encoder_hidden_states=encoder_hidden_states)
+        hidden_states = self.proj_out(hidden_states)
+        hidden_states = (hidden_states[None, None, :].reshape(batch_size, height, width, num_frames, channel)
+                         .permute(0, 3, 4, 1, 2).contiguous())
+        hidden_states = hidden_states.reshape(batch_frames, channel, height, width)
+        return (hidden_states + residual,)
+
+
+class DownBlock3D(nn.Module):
+    has_cross_attention = False
+
+    def __init__(self, in_channels, out_channels, temb_channels, num_layers=1, resnet_eps=1e-6, resnet_groups=32,
+                 output_scale_factor=1.0, add_downsample=True, downsample_padding=1, **_unused):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(in_channels=in_channels if i == 0 else out_channels,
+                                                    out_channels=out_channels, temb_channels=temb_channels,
+                                                    eps=resnet_eps, groups=resnet_groups,
+                                                    output_scale_factor=output_scale_factor) for i in range(num_layers)])
+        self.temp_convs = nn.ModuleList([TemporalConvLayer(out_channels, out_channels, dropout=0.1,
+                                                           norm_num_groups=resnet_groups) for _ in range(num_layers)])
+        self.downsamplers = None
+        if add_downsample:
+            self.downsamplers = nn.ModuleList([Downsample2D(out_channels, use_conv=True, out_channels=out_channels,
+                                                            padding=downsample_padding, name="op")])
+
+    def forward(self, hidden_states, temb=None, num_frames=1, **_kw):
+        output_states = ()
+        for resnet, temp_conv in zip(self.resnets, self.temp_convs):
+            hidden_states = resnet(hidden_states, temb)
+            hidden_states = temp_conv(hidden_states, num_frames=num_frames)
+            output_states += (hidden_states,)
+        if self.downsamplers is not None:
+            for d in self.downsamplers:
+                hidden_states = d(hidden_states)
+            output_states += (hidden_states,)
+        return hidden_states, output_states
+
+
+class CrossAttnDownBlock3D(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels, out_channels, temb_channels, num_layers=1, resnet_eps=1e-6, resnet_groups=32,
+                 num_attention_heads=1, cross_attention_dim=1280, output_scale_factor=1.0, downsample_padding=1,
+                 add_downsample=True, use_linear_projection=False, only_cross_attention=False, upcast_attention=False,
+                 **_unused):
+        super().__init__()
+        self.num_attention_heads = num_attention_heads
+        resnets, temp_convs, attentions, temp_attentions = [], [], [], []
+        for i in range(num_layers):
+            resnets.append(ResnetBlock2D(in_channels=in_channels if i == 0 else out_channels, out_channels=out_channels,
+                                         temb_channels=temb_channels, eps=resnet_eps, groups=resnet_groups,
+                                         output_scale_factor=output_scale_factor))
+            temp_convs.append(TemporalConvLayer(out_channels, out_channels, dropout=0.1, norm_num_groups=resnet_groups))
+            # NB positional order (heads, head_dim) = (out_channels // num_attention_heads, num_attention_heads)
+            attentions.append(Transformer2DModel(out_channels // num_attention_heads, num_attention_heads,
+                                                 in_channels=out_channels, num_layers=1,
+                                                 cross_attention_dim=cross_attention_dim, norm_num_groups=resnet_groups,
+                                                 use_linear_projection=use_linear_projection,
+                                                 only_cross_attention=only_cross_attention,
+                                                 upcast_attention=upcast_attention))
+            temp_attentions.append(TransformerTemporalModel(out_channels // num_attention_heads, num_attention_heads,
+                                                            in_channels=out_channels, num_layers=1,
+                                                            cross_attention_dim=cross_attention_dim,
+                                                            norm_num_groups=resnet_groups))
+        self.resnets = nn.ModuleList(resnets)
+        self.temp_convs = nn.ModuleList(temp_convs)
+        self.attentions = nn.ModuleList(attentions)
+        self.temp_attentions = nn.ModuleList(temp_attentions)
+        self.downsamplers = None
+        if add_downsample:
+            self.downsamplers = nn.ModuleList([Downsample2D(out_channels, use_conv=True, out_channels=out_channels,
+                                                            padding=downsample_padding, name="op")])
+
+    def forward(self, hidden_states, temb=None, encoder_hidden_states=None, num_frames=1, **_kw):
+        output_states = ()
+        for resnet, temp_conv, attn, temp_attn in zip(self.resnets, self.temp_convs, self.attentions, self.temp_attentions):
+            hidden_states = resnet(hidden_states, temb)
+            hidden_states = temp_conv(hidden_states, num_frames=num_frames)
+            hidden_states = attn(hidden_states, encoder_hidden_states=encoder_hidden_states)[0]
+            hidden_states = temp_attn(hidden_states, num_frames=num_frames)[0]
+            output_states += (hidden_states,)
+        if self.downsamplers is not None:
+            for d in self.downsamplers:
+                hidden_states = d(hidden_states)
+            output_states += (hidden_states,)
+        return hidden_states, output_states
+
+
+class UNetMidBlock3DCrossAttn(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels, temb_channels, num_layers=1, resnet_eps=1e-6, resnet_groups=32,
+                 num_attention_heads=1, output_scale_factor=1.0, cross_attention_dim=1280, use_linear_projection=True,
+                 upcast_attention=False, **_unused):
+        super().__init__()
+        resnets = [ResnetBlock2D(in_channels=in_channels, out_channels=in_channels, temb_channels=temb_channels,
+                                 eps=resnet_eps, groups=resnet_groups, output_scale_factor=output_scale_factor)]
+        temp_convs = [TemporalConvLayer(in_channels, in_channels, dropout=0.1, norm_num_groups=resnet_groups)]
+        attentions, temp_attentions = [], []
+        for _ in range(num_layers):
+            attentions.append(Transformer2DModel(in_channels // num_attention_heads, num_attention_heads,
+                                                 in_channels=in_channels, num_layers=1,
+                                                 cross_attention_dim=cross_attention_dim, norm_num_groups=resnet_groups,
+                                                 use_linear_projection=use_linear_projection,
+                                                 upcast_attention=upcast_attention))
+            temp_attentions.append(TransformerTemporalModel(in_channels // num_attention_heads, num_attention_heads,
+                                                            in_channels=in_channels, num_layers=1,
+                                                            cross_attention_dim=cross_attention_dim,
+                                                            norm_num_groups=resnet_groups))
+            resnets.append(ResnetBlock2D(in_channels=in_channels, out_channels=in_channels, temb_channels=temb_channels,
+                                         eps=resnet_eps, groups=resnet_groups, output_scale_factor=output_scale_factor))
+            temp_convs.append(TemporalConvLayer(in_channels, in_channels, dropout=0.1, norm_num_groups=resnet_groups))
+        self.resnets = nn.ModuleList(resnets)
+        self.temp_convs = nn.ModuleList(temp_convs)
+        self.attentions = nn.ModuleList(attentions)
+        self.temp_attentions = nn.ModuleList(temp_attentions)
+
+    def forward(self, hidden_states, temb=None, encoder_hidden_states=None, num_frames=1, **_kw):
+        hidden_states = self.resnets[0](hidden_states, temb)
+        hidden_states = self.temp_convs[0](hidden_states, num_frames=num_frames)
+        for attn, temp_attn, resnet, temp_conv in zip(self.attentions, self.temp_attentions, self.resnets[1:],
+                                                      self.temp_convs[1:]):
+            hidden_states = attn(hidden_states, encoder_hidden_states=encoder_hidden_states)[0]
+            hidden_states = temp_attn(hidden_states, num_frames=num_frames)[0]
+            hidden_states = resnet(hidden_states, temb)
+            hidden_states = temp_conv(hidden_states, num_frames=num_frames)
+        return hidden_states
+
+
+class UpBlock3D(nn.Module):
+    has_cross_attention = False
+
+    def __init__(self, in_channels, prev_output_channel, out_channels, temb_channels, num_layers=1, resnet_eps=1e-6,
+                 resnet_groups=32, output_scale_factor=1.0, add_upsample=True, **_unused):
+        super().__init__()
+        resnets, temp_convs = [], []
+        for i in range(num_layers):
+            res_skip_channels = in_channels if (i == num_layers - 1) else out_channels
+            resnet_in_channels = prev_output_channel if i == 0 else out_channels
+            resnets.append(ResnetBlock2D(in_channels=resnet_in_channels + res_skip_channels, out_channels=out_channels,
+                                         temb_channels=temb_channels, eps=resnet_eps, groups=resnet_groups,
+                                         output_scale_factor=output_scale_factor))
+            temp_convs.append(TemporalConvLayer(out_channels, out_channels, dropout=0.1, norm_num_groups=resnet_groups))
+        self.resnets = nn.ModuleList(resnets)
+        self.temp_convs = nn.ModuleList(temp_convs)
+        self.upsamplers = None
+        if add_upsample:
+            self.upsamplers = nn.ModuleList([Upsample2D(out_channels, use_conv=True, out_channels=out_channels)])
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb=None, upsample_size=None, num_frames=1, **_kw):
+        for resnet, temp_conv in zip(self.resnets, self.temp_convs):
+            res_hidden_states = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = torch.cat([hidden_states, res_hidden_states], dim=1)
+            hidden_states = resnet(hidden_states, temb)
+            hidden_states = temp_conv(hidden_states, num_frames=num_frames)
+        if self.upsamplers is not None:
+            for u in self.upsamplers:
+                hidden_states = u(hidden_states, upsample_size)
+        return hidden_states
+
+
+class CrossAttnUpBlock3D(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels, out_channels, prev_output_channel, temb_channels, num_layers=1, resnet_eps=1e-6,
+                 resnet_groups=32, num_attention_heads=1, cross_attention_dim=1280, output_scale_factor=1.0,
+                 add_upsample=True, use_linear_projection=False, only_cross_attention=False, upcast_attention=False,
+                 **_unused):
+        super().__init__()
+        resnets, temp_convs, attentions, temp_attentions = [], [], [], []
+        for i in range(num_layers):
+            res_skip_channels = in_channels if (i == num_layers - 1) else out_channels
+            resnet_in_channels = prev_output_channel if i == 0 else out_channels
+            resnets.append(ResnetBlock2D(in_channels=resnet_in_channels + res_skip_channels, out_channels=out_channels,
+                                         temb_channels=temb_channels, eps=resnet_eps, groups=resnet_groups,
+                                         output_scale_factor=output_scale_factor))
+            temp_convs.append(TemporalConvLayer(out_channels, out_channels, dropout=0.1, norm_num_groups=resnet_groups))
+            attentions.append(Transformer2DModel(out_channels // num_attention_heads, num_attention_heads,
+                                                 in_channels=out_channels, num_layers=1,
+                                                 cross_attention_dim=cross_attention_dim, norm_num_groups=resnet_groups,
+                                                 use_linear_projection=use_linear_projection,
+                                                 only_cross_attention=only_cross_attention,
+                                                 upcast_attention=upcast_attention))
+            temp_attentions.append(TransformerTemporalModel(out_channels // num_attention_heads, num_attention_heads,
+                                                            in_channels=out_channels, num_layers=1,
+                                                            cross_attention_dim=cross_attention_dim,
+                                                            norm_num_groups=resnet_groups))
+        self.resnets = nn.ModuleList(resnets)
+        self.temp_convs = nn.ModuleList(temp_convs)
+        self.attentions = nn.ModuleList(attentions)
+        self.temp_attentions = nn.ModuleList(temp_attentions)
+        self.upsamplers = None
+        if add_upsample:
+            self.upsamplers = nn.ModuleList([Upsample2D(out_channels, use_conv=True, out_channels=out_channels)])
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb=None, encoder_hidden_states=None,
+                upsample_size=None, num_frames=1, **_kw):
+        for resnet, temp_conv, attn, temp_attn in zip(self.resnets, self.temp_convs, self.attentions, self.temp_attentions):
+            res_hidden_states = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = torch.cat([hidden_states, res_hidden_states], dim=1)
+            hidden_states = resnet(hidden_states, temb)
+            hidden_states = temp_conv(hidden_states, num_frames=num_frames)
+            hidden_states = attn(hidden_states, encoder_hidden_states=encoder_hidden_states)[0]
+            hidden_states = temp_attn(hidden_states, num_frames=num_frames)[0]
+        if self.upsamplers is not None:
+            for u in self.upsamplers:
+                hidden_states = u(hidden_states, upsample_size)
+        return hidden_states
+
+
+def get_down_block_3d(down_block_type, num_layers, in_channels, out_channels, temb_channels, add_downsample, resnet_eps,
+                      resnet_act_fn="silu", num_attention_heads=None, resnet_groups=None, cross_attention_dim=None,
+                      downsample_padding=None, dual_cross_attention=False, use_linear_projection=True,
+                      only_cross_attention=False, upcast_attention=False, **_unused):
+    """unet_3d_blocks.get_down_block (note the 3-D default use_linear_projection=True)."""
+    if down_block_type == "DownBlock3D":
+        return DownBlock3D(num_layers=num_layers, in_channels=in_channels, out_channels=out_channels,
+                           temb_channels=temb_channels, add_downsample=add_downsample, resnet_eps=resnet_eps,
+                           resnet_groups=resnet_groups, downsample_padding=downsample_padding)
+    if down_block_type == "CrossAttnDownBlock3D":
+        return CrossAttnDownBlock3D(num_layers=num_layers, in_channels=in_channels, out_channels=out_channels,
+                                    temb_channels=temb_channels, add_downsample=add_downsample, resnet_eps=resnet_eps,
+                                    resnet_groups=resnet_groups, downsample_padding=downsample_padding,
+                                    cross_attention_dim=cross_attention_dim, num_attention_heads=num_attention_heads,
+                                    use_linear_projection=use_linear_projection,
+                                    only_cross_attention=only_cross_attention, upcast_attention=upcast_attention)
+    raise ValueError(f"{down_block_type} does not exist.")
+
+
+def get_up_block_3d(up_block_type, num_layers, in_channels, out_channels, prev_output_channel, temb_channels,
+                    add_upsample, resnet_eps, resnet_act_fn="silu", num_attention_heads=None, resnet_groups=None,
+                    cross_attention_dim=None, dual_cross_attention=False, use_linear_projection=True,
+                    only_cross_attention=False, upcast_attention=False, **_unused):
+    if up_block_type == "UpBlock3D":
+        return UpBlock3D(num_layers=num_layers, in_channels=in_channels, out_channels=out_channels,
+                         prev_output_channel=prev_output_channel, temb_channels=temb_channels, add_upsample=add_upsample,
+                         resnet_eps=resnet_eps, resnet_groups=resnet_groups)
+    if up_block_type == "CrossAttnUpBlock3D":
+        return CrossAttnUpBlock3D(num_layers=num_layers, in_channels=in_channels, out_channels=out_channels,
+                                  prev_output_channel=prev_output_channel, temb_channels=temb_channels,
+                                  add_upsample=add_upsample, resnet_eps=resnet_eps, resnet_groups=resnet_groups,
+                                  cross_attention_dim=cross_attention_dim, num_attention_heads=num_attention_heads,
+                                  use_linear_projection=use_linear_projection,
+                                  only_cross_attention=only_cross_attention, upcast_attention=upcast_attention)
     raise ValueError(f"{up_block_type} does not exist.")

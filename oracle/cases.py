@@ -72,3 +72,18 @@ def unet_sdxl_inputs(n: int = 2, r: int = 16, seed: int = 0, with_residuals: boo
                                        time_ids=torch.tensor([[8.0 * r, 8.0 * r, 0, 0, 8.0 * r, 8.0 * r]] * n)),
                 down_block_additional_residuals=res if with_residuals else None,
                 mid_block_additional_residual=0 if with_residuals else None)
+
+
+def unet_i2vgen_inputs(b: int = 1, f: int = 4, r: int = 16, seed: int = 0, with_residuals: bool = True):
+    """I2VGen-XL UNet inputs: sample (b,4,f,r,r), image_latents (b,4,f,r,r), image_embeddings (b,1024) -- the pipeline
+    passes (2,1,1024) and `.view(-1, 4, 1024)` flattens it --, text states (b,77,1024), fps (b,)."""
+    res = mid = None
+    if with_residuals:
+        down, mid = controlnet_residuals(b * f, r, seed)
+        res = [d * 0.5 for d in down]
+        mid = mid * 0.5
+    return dict(sample=seeded_tensor("i2v_sample", (b, 4, f, r, r), seed), timestep=torch.tensor(961.0),
+                fps=torch.tensor([16.0] * b), image_latents=seeded_tensor("i2v_image_latents", (b, 4, f, r, r), seed),
+                image_embeddings=seeded_tensor("i2v_image_embeddings", (b, 1, 1024), seed),
+                encoder_hidden_states=seeded_tensor("i2v_ehs", (b, 77, 1024), seed),
+                down_block_additional_residuals=res, mid_block_additional_residual=mid)

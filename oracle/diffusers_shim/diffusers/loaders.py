@@ -4,3 +4,7 @@ class FromOriginalControlNetMixin:
 
 class LoraLoaderMixin:
     pass
+
+
+class UNet2DConditionLoadersMixin:
+    pass

@@ -1,1 +1,1 @@
-from oracle.blocks import BasicTransformerBlock, TemporalBasicTransformerBlock  # noqa: F401
+from oracle.blocks import BasicTransformerBlock, TemporalBasicTransformerBlock, TransformerTemporalModel  # noqa: F401

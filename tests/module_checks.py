@@ -170,10 +170,129 @@ def check_router():
     return _compare("ControlNetRouter masked softmax", ours, ref, None, tol_rel=1e-5, tol_max=1e-5)
 
 
+def check_unet_i2vgen(b=1, f=4, r=32, with_residuals=True):
+    from ctrl_adapter_b200.unet_i2vgen import I2VGenXLUNet
+    from oracle import cases
+    from oracle.unet_i2vgen import I2VGenXLUNet as OUNet
+    inputs = cases.unet_i2vgen_inputs(b, f, r, with_residuals=with_residuals)
+    call = lambda m, i: m(**i)  # noqa: E731
+    sd, ref, eager, inp16 = _oracle_runs(lambda: OUNet(), 7, inputs, call)
+    ours_m = I2VGenXLUNet()
+    ours_m.load_state_dict(sd)
+    ours_m = ours_m.to(BF16).cuda().eval()
+    ours = ours_m(**inp16)
+    torch.cuda.synchronize()
+    return _compare(f"I2VGenXLUNet b={b} f={f} r={r} residuals={int(with_residuals)}", ours, ref, eager,
+                    tol_rel=3e-2, tol_max=8e-2)
+
+
+def _build_pair(make_oracle, make_ours, seed):
+    """oracle (fp32, bf16-quantised weights, on GPU) and our module with identical weights."""
+    from oracle.weights import seeded_init_
+    o = seeded_init_(make_oracle(), seed).eval()
+    sd = {k: v.clone() for k, v in o.state_dict().items()}
+    for p_ in o.parameters():
+        p_.data = _q(p_.data)
+    m = make_ours()
+    m.load_state_dict(sd)
+    return o.cuda(), m.to(BF16).cuda().eval()
+
+
+def check_step_sdxl(steps=2):
+    """Whole SDXL denoising iterations (ControlNet -> adapter -> UNet -> CFG -> Euler) vs the restated reference loop
+    (oracle/pipeline_sdxl.py) in fp32, B=1 at the real 1024x1024 geometry (the 2x adapter only fits 128^2 latents)."""
+    from ctrl_adapter_b200.adapter import ControlNetAdapter
+    from ctrl_adapter_b200.controlnet import ControlNetModel
+    from ctrl_adapter_b200.pipeline_sdxl import SDXLControlNetAdapterLoop
+    from ctrl_adapter_b200.unet_sdxl import UNet2DConditionModel
+    from oracle import cases
+    from oracle.adapter import ControlNetAdapter as OA
+    from oracle.controlnet import ControlNetModel as OC
+    from oracle.pipeline_sdxl import EulerDiscreteScheduler, sdxl_step
+    from oracle.unet_sdxl import UNet2DConditionModel as OU
+    from oracle.weights import seeded_tensor
+    ocn, cn = _build_pair(lambda: OC(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 4)
+    oad, ad = _build_pair(lambda: OA(**cases.ADAPTER_SDXL_KW), lambda: ControlNetAdapter(**cases.ADAPTER_SDXL_KW), 1)
+    oun, un = _build_pair(lambda: OU(), lambda: UNet2DConditionModel(), 6)
+    b = 1
+    inp = dict(latents=seeded_tensor("s_lat", (b, 4, 128, 128)), prompt_embeds=seeded_tensor("s_pe", (2 * b, 77, 2048)),
+               add_text_embeds=seeded_tensor("s_te", (2 * b, 1280)),
+               add_time_ids=torch.tensor([[1024.0, 1024, 0, 0, 1024, 1024]] * (2 * b)),
+               controlnet_prompt_embeds=seeded_tensor("s_cpe", (2 * b, 77, 768)),
+               control_images=torch.sigmoid(seeded_tensor("s_img", (2 * b, 3, 512, 512))))
+    inp = {k: _q(v).cuda() for k, v in inp.items()}
+    sch = EulerDiscreteScheduler()
+    sch.set_timesteps(50, device="cuda")
+    loop = SDXLControlNetAdapterLoop(cn, ad, un, num_inference_steps=50, guidance_scale=5.0)
+    loop.prepare(**inp)
+    lat = _q(inp["latents"] * sch.init_noise_sigma)
+    with torch.no_grad():
+        for i in range(steps):
+            lat = sdxl_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["add_text_embeds"], inp["add_time_ids"],
+                            inp["controlnet_prompt_embeds"], inp["control_images"])
+            loop.step(i)
+    torch.cuda.synchronize()
+    return _compare(f"SDXL denoise loop, {steps} steps, B=1 1024x1024", loop.latents, lat, None, tol_rel=2e-2, tol_max=8e-2)
+
+
+def check_step_i2vgen(steps=2, multi=False):
+    """Whole I2VGen-XL iterations (ControlNet[s] -> [router merge] -> adapter -> UNet -> CFG -> DDIM), B=1, F=4, 32^2."""
+    from ctrl_adapter_b200.adapter import ControlNetAdapter, ControlNetRouter
+    from ctrl_adapter_b200.controlnet import ControlNetModel, MultiControlNetModel
+    from ctrl_adapter_b200.pipeline_i2vgen import I2VGenXLControlNetAdapterLoop
+    from ctrl_adapter_b200.unet_i2vgen import I2VGenXLUNet
+    from oracle import cases
+    from oracle.adapter import ControlNetAdapter as OA, ControlNetRouter as OR
+    from oracle.controlnet import ControlNetModel as OC, MultiControlNetModel as OM
+    from oracle.pipeline_i2vgen import DDIMScheduler, i2vgen_step
+    from oracle.unet_i2vgen import I2VGenXLUNet as OU
+    from oracle.weights import seeded_tensor
+    b, f, r = 1, 4, 32
+    kw = dict(cases.ADAPTER_VIDEO_KW, num_frames=f)
+    oad, ad = _build_pair(lambda: OA(**kw), lambda: ControlNetAdapter(**kw), 2)
+    oun, un = _build_pair(lambda: OU(), lambda: I2VGenXLUNet(), 7)
+    router = orouter = masks = None
+    n = 2 * b * f
+    if multi:
+        nets = [_build_pair(lambda: OC(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 40 + k)
+                for k in range(2)]
+        ocn, cn = OM([p_[0] for p_ in nets]), MultiControlNetModel([p_[1] for p_ in nets])
+        rk = dict(cases.ROUTER_KW, num_experts=3)
+        orouter, router = _build_pair(lambda: OR(**rk), lambda: ControlNetRouter(**rk), 3)
+        masks = [1, 1, 0]
+        images = [torch.sigmoid(seeded_tensor(f"v_img{k}", (n, 3, 8 * r, 8 * r))) for k in range(2)]
+    else:
+        ocn, cn = _build_pair(lambda: OC(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 4)
+        images = torch.sigmoid(seeded_tensor("v_img", (n, 3, 8 * r, 8 * r)))
+    inp = dict(latents=seeded_tensor("v_lat", (b, 4, f, r, r)), prompt_embeds=seeded_tensor("v_pe", (2 * b, 77, 1024)),
+               image_latents=seeded_tensor("v_il", (2 * b, 4, f, r, r)),
+               image_embeddings=seeded_tensor("v_ie", (2 * b, 1, 1024)), fps=torch.tensor([16.0] * (2 * b)),
+               controlnet_prompt_embeds=seeded_tensor("v_cpe", (n, 77, 768)))
+    inp = {k: _q(v).cuda() for k, v in inp.items()}
+    images = [_q(i).cuda() for i in images] if multi else _q(images).cuda()
+    sch = DDIMScheduler()
+    sch.set_timesteps(50, device="cuda")
+    loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, router, num_inference_steps=50, guidance_scale=9.0,
+                                         inference_expert_masks=masks)
+    loop.prepare(control_images=images, **inp)
+    lat = inp["latents"]
+    with torch.no_grad():
+        for i in range(steps):
+            lat = i2vgen_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["image_latents"],
+                              inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"], images,
+                              router=orouter, masks=masks)
+            loop.step(i)
+    torch.cuda.synchronize()
+    return _compare(f"I2VGen-XL denoise loop multi={int(multi)}, {steps} steps, B=1 F=4 32x32", loop.latents_bcfhw(), lat,
+                    None, tol_rel=2e-2, tol_max=8e-2)
+
+
 GROUPS = {
     "adapter": [lambda: check_adapter("sdxl", 2, 8), lambda: check_adapter("video", 1, 8, 4), check_router],
     "controlnet": [lambda: check_controlnet(2, 8), lambda: check_controlnet(2, 16, True, 0.75)],
     "unet": [lambda: check_unet_sdxl(2, 16, True), lambda: check_unet_sdxl(1, 32, False)],
+    "video": [lambda: check_unet_i2vgen(1, 4, 32, True), lambda: check_unet_i2vgen(2, 2, 32, False)],
+    "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
 }
 
 
