@@ -43,6 +43,8 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=8, help="images per GPU (BASELINE config: 8)")
     p.add_argument("--res", type=int, default=1024)
+    p.add_argument("--workload", default="sdxl", choices=["sdxl", "i2vgen"],
+                   help="sdxl = BASELINE.json configs[1] (headline); i2vgen = configs[2] (I2VGen-XL 16f 512x512, batch 4)")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     p.add_argument("--skip-cpu-baseline", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -229,18 +231,49 @@ def main():
     torch.manual_seed(1234 + rank)
     with torch.device(dev):
         cn = ControlNetModel(cross_attention_dim=768)
-        ad = ControlNetAdapter("sdxl", num_blocks=1, num_frames=1, cross_attention_dim=2048, add_spatial_resnet=True,
-                               add_spatial_transformer=True, add_adapter_location_A=True, add_adapter_location_B=True,
-                               add_adapter_location_C=True)
-        un = UNet2DConditionModel()
     # zero-initialised ControlNet heads would make every residual exactly 0: give them random values
     for m in list(cn.controlnet_down_blocks) + [cn.controlnet_mid_block, cn.controlnet_cond_embedding.conv_out]:
         torch.nn.init.normal_(m.weight, std=0.02)
-    cn, ad, un = (m.to(BF16).eval() for m in (cn, ad, un))
-    loop = SDXLControlNetAdapterLoop(cn, ad, un, num_inference_steps=50, guidance_scale=5.0,
-                                     controlnet_conditioning_scale=1.0)
-    inp = synthetic_inputs(a.batch, a.res, dev, 1234 + rank)
-    loop.prepare(**inp)
+    if a.workload == "sdxl":
+        with torch.device(dev):
+            ad = ControlNetAdapter("sdxl", num_blocks=1, num_frames=1, cross_attention_dim=2048, add_spatial_resnet=True,
+                                   add_spatial_transformer=True, add_adapter_location_A=True,
+                                   add_adapter_location_B=True, add_adapter_location_C=True)
+            un = UNet2DConditionModel()
+        cn, ad, un = (m.to(BF16).eval() for m in (cn, ad, un))
+        loop = SDXLControlNetAdapterLoop(cn, ad, un, num_inference_steps=50, guidance_scale=5.0,
+                                         controlnet_conditioning_scale=1.0)
+        inp = synthetic_inputs(a.batch, a.res, dev, 1234 + rank)
+        loop.prepare(**inp)
+        n_samples = 2 * a.batch
+        tflop_per_sample = TFLOP_PER_SAMPLE
+        wl_name = (f"SDXL+depth ControlNet+Ctrl-Adapter {a.res}x{a.res}, batch {a.batch} per GPU "
+                   f"(CFG: {n_samples} frame-samples), one pipeline-loop iteration per step")
+        base_cfg = "BASELINE.json configs[1]"
+    else:
+        from ctrl_adapter_b200.pipeline_i2vgen import I2VGenXLControlNetAdapterLoop
+        from ctrl_adapter_b200.unet_i2vgen import I2VGenXLUNet
+        frames, vb = 16, (a.batch if a.batch != 8 else 4)
+        with torch.device(dev):
+            ad = ControlNetAdapter("i2vgenxl", num_blocks=1, num_frames=frames, cross_attention_dim=1024,
+                                   add_spatial_resnet=True, add_temporal_resnet=True, add_spatial_transformer=True,
+                                   add_temporal_transformer=True, add_adapter_location_A=True,
+                                   add_adapter_location_B=True, add_adapter_location_C=True,
+                                   add_adapter_location_D=True, add_adapter_location_M=True)
+            un = I2VGenXLUNet()
+        cn, ad, un = (m.to(BF16).eval() for m in (cn, ad, un))
+        loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, None, num_inference_steps=50, guidance_scale=9.0)
+        g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+        r = lambda *s_: torch.randn(*s_, generator=g).to(dev)  # noqa: E731
+        n_samples = 2 * vb * frames
+        loop.prepare(latents=r(vb, 4, frames, 64, 64), prompt_embeds=r(2 * vb, 77, 1024),
+                     image_latents=r(2 * vb, 4, frames, 64, 64), image_embeddings=r(2 * vb, 1, 1024),
+                     fps=torch.full((2 * vb,), 16.0, device=dev), controlnet_prompt_embeds=r(n_samples, 77, 768),
+                     control_images=torch.rand(n_samples, 3, 512, 512, generator=g).to(dev))
+        tflop_per_sample = 0.2833 + 0.6564 + 1.308  # ControlNet, video adapter, I2VGen-XL UNet (rough)
+        wl_name = (f"I2VGen-XL+depth ControlNet+Ctrl-Adapter 16 frames 512x512, batch {vb} per GPU "
+                   f"(CFG: {n_samples} frame-samples), one pipeline-loop iteration per step")
+        base_cfg = "BASELINE.json configs[2]"
 
     use_graph = not a.no_graph
     l0 = ops.PROFILER.launches
@@ -349,7 +382,7 @@ def main():
                         "how": f"algorithmic bytes / CUDA-event time of one step; peak {peak_src}"}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not a.skip_cpu_baseline:
+    if rank == 0 and world == 1 and not a.skip_cpu_baseline and a.workload == "sdxl":
         try:
             del loop
             torch.cuda.empty_cache()
@@ -358,16 +391,14 @@ def main():
             cpu_baseline = {"value": None, "error": repr(e)[:300]}
 
     if rank == 0:
-        n_samples = 2 * a.batch
-        step_tflop = n_samples * TFLOP_PER_SAMPLE
+        step_tflop = n_samples * tflop_per_sample
         line = {
-            "metric": "denoising steps/sec (SDXL 1024x1024 + depth ControlNet + Ctrl-Adapter, batch 8)",
+            "metric": "denoising steps/sec (SDXL 1024x1024 + depth ControlNet + Ctrl-Adapter, batch 8)" if a.workload == "sdxl"
+            else "denoising steps/sec (I2VGen-XL 16f 512x512 + depth ControlNet + Ctrl-Adapter, batch 4)",
             "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"SDXL+depth ControlNet+Ctrl-Adapter {a.res}x{a.res}, batch {a.batch} per GPU "
-                                   f"(CFG: {n_samples} frame-samples), one pipeline-loop iteration per step",
-                       "baseline_config": "BASELINE.json configs[1]", "parallelism": f"batch-sharded dp{world}",
+            "config": {"workload": wl_name, "baseline_config": base_cfg, "parallelism": f"batch-sharded dp{world}",
                        "cuda_graph": use_graph, "l2": "per-step working set (6.3 GB bf16 weights + multi-GB activations) "
                                                       "exceeds the 126 MB L2; no explicit flush",
                        "algorithmic_tflop_per_step": round(step_tflop, 1),

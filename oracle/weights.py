@@ -23,9 +23,12 @@ def _std_for(name: str, p: torch.Tensor) -> float:
 @torch.no_grad()
 def seeded_init_(module: torch.nn.Module, seed: int = 0) -> torch.nn.Module:
     for name, p in sorted(module.named_parameters(), key=lambda kv: kv[0]):
-        g = torch.Generator(device="cpu")
+        # CPU parameters use the CPU generator (the stream the committed golden vectors were produced with);
+        # parameters that already live on a GPU are filled there (GPU-only parity tests: much faster for 10^9 weights,
+        # both sides of those tests share the values through a state_dict copy)
+        g = torch.Generator(device=p.device if p.is_cuda else "cpu")
         g.manual_seed((zlib.crc32(name.encode()) + 7919 * seed) & 0x7FFFFFFF)
-        v = torch.randn(p.shape, generator=g, dtype=torch.float32)
+        v = torch.randn(p.shape, generator=g, dtype=torch.float32, device=p.device if p.is_cuda else "cpu")
         leaf = name.rsplit(".", 1)[-1]
         is_norm_weight = leaf == "weight" and p.dim() == 1
         if name.endswith("mix_factor"):

@@ -85,11 +85,12 @@ def _compare(name, ours, ref, eager=None, tol_rel=2e-2, tol_max=6e-2, extra=None
 def _oracle_runs(make_oracle, seed, inputs, call):
     """fp32 truth (bf16-quantised weights/inputs) and eager bf16-autocast runs of the oracle on the GPU."""
     from oracle.weights import seeded_init_
-    m = seeded_init_(make_oracle(), seed).eval()
+    with torch.device("cuda"):
+        m = make_oracle()
+    m = seeded_init_(m, seed).eval()
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     for p in m.parameters():
         p.data = _q(p.data)
-    m = m.cuda()
     inp32 = _map(inputs, lambda t: _q(t).cuda() if t.is_floating_point() else t.cuda())
     with torch.no_grad():
         ref = call(m, inp32)
@@ -114,9 +115,10 @@ def check_adapter(kind="sdxl", n=2, r=8, frames=4):
         kw, inputs, seed = dict(cases.ADAPTER_VIDEO_KW, num_frames=frames), cases.adapter_video_inputs(n, frames, r), 2
     call = lambda m, i: m(**i)  # noqa: E731
     sd, ref, eager, inp16 = _oracle_runs(lambda: OAdapter(**kw), seed, inputs, call)
-    ours_m = ControlNetAdapter(**kw)
+    with torch.device("cuda"):
+        ours_m = ControlNetAdapter(**kw)
     ours_m.load_state_dict(sd)
-    ours_m = ours_m.to(BF16).cuda().eval()
+    ours_m = ours_m.to(BF16).eval()
     ours = ours_m(**inp16)
     torch.cuda.synchronize()
     # unselected blocks must come back as zero tensors of the input's shape, mid None for SDXL
@@ -130,9 +132,10 @@ def check_controlnet(n=2, r=8, skip_conv_in=False, scale=1.0):
     inputs = dict(cases.controlnet_inputs(n, r), skip_conv_in=skip_conv_in, conditioning_scale=scale)
     call = lambda m, i: m(**i)  # noqa: E731
     sd, ref, eager, inp16 = _oracle_runs(lambda: OCN(**cases.CONTROLNET_KW), 4, inputs, call)
-    ours_m = ControlNetModel(**cases.CONTROLNET_KW)
+    with torch.device("cuda"):
+        ours_m = ControlNetModel(**cases.CONTROLNET_KW)
     ours_m.load_state_dict(sd)
-    ours_m = ours_m.to(BF16).cuda().eval()
+    ours_m = ours_m.to(BF16).eval()
     ours = ours_m(**inp16)
     torch.cuda.synchronize()
     return _compare(f"ControlNetModel n={n} r={r} skip_conv_in={int(skip_conv_in)} scale={scale}", ours, ref, eager)
@@ -145,9 +148,10 @@ def check_unet_sdxl(n=2, r=16, with_residuals=True):
     inputs = cases.unet_sdxl_inputs(n, r, with_residuals=with_residuals)
     call = lambda m, i: m(**i)  # noqa: E731
     sd, ref, eager, inp16 = _oracle_runs(lambda: OUNet(), 6, inputs, call)
-    ours_m = UNet2DConditionModel()
+    with torch.device("cuda"):
+        ours_m = UNet2DConditionModel()
     ours_m.load_state_dict(sd)
-    ours_m = ours_m.to(BF16).cuda().eval()
+    ours_m = ours_m.to(BF16).eval()
     ours = ours_m(**inp16)
     torch.cuda.synchronize()
     return _compare(f"UNet2DConditionModel[sdxl] n={n} r={r} residuals={int(with_residuals)}", ours, ref, eager,
@@ -177,9 +181,10 @@ def check_unet_i2vgen(b=1, f=4, r=32, with_residuals=True):
     inputs = cases.unet_i2vgen_inputs(b, f, r, with_residuals=with_residuals)
     call = lambda m, i: m(**i)  # noqa: E731
     sd, ref, eager, inp16 = _oracle_runs(lambda: OUNet(), 7, inputs, call)
-    ours_m = I2VGenXLUNet()
+    with torch.device("cuda"):
+        ours_m = I2VGenXLUNet()
     ours_m.load_state_dict(sd)
-    ours_m = ours_m.to(BF16).cuda().eval()
+    ours_m = ours_m.to(BF16).eval()
     ours = ours_m(**inp16)
     torch.cuda.synchronize()
     return _compare(f"I2VGenXLUNet b={b} f={f} r={r} residuals={int(with_residuals)}", ours, ref, eager,
@@ -189,13 +194,14 @@ def check_unet_i2vgen(b=1, f=4, r=32, with_residuals=True):
 def _build_pair(make_oracle, make_ours, seed):
     """oracle (fp32, bf16-quantised weights, on GPU) and our module with identical weights."""
     from oracle.weights import seeded_init_
-    o = seeded_init_(make_oracle(), seed).eval()
-    sd = {k: v.clone() for k, v in o.state_dict().items()}
+    with torch.device("cuda"):
+        o = make_oracle()
+        m = make_ours()
+    o = seeded_init_(o, seed).eval()
+    m.load_state_dict(o.state_dict())
     for p_ in o.parameters():
         p_.data = _q(p_.data)
-    m = make_ours()
-    m.load_state_dict(sd)
-    return o.cuda(), m.to(BF16).cuda().eval()
+    return o, m.to(BF16).eval()
 
 
 def check_step_sdxl(steps=2):
