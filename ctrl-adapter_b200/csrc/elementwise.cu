@@ -429,14 +429,21 @@ cudaError_t launch_i2vgen_latent_encoder(const __nv_bfloat16* x, int clips, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Temporal self-attention: sequence = the F frames of one pixel, head dim 64.  HBM-bound (every Q/K/V element is
-// read once), so plain FMA: one warp per (clip, pixel, head); lane i owns head-dim elements {2i, 2i+1}.
-// Layout [clip][frame][pixel][heads*64]; frames <= 32.
+// Temporal self-attention: sequence = the F frames of one pixel, head dim 64.  HBM-bound (every Q/K/V element is read
+// once), so plain FMA.  One warp per (clip, pixel, head).
+//   frames <= 16: lane = (query frame i = lane >> 1, half = lane & 1 of the head dim): each lane holds q[i][32 dims],
+//                 walks the F keys (K rows are shared by all lanes -> L1 broadcast), one shuffle per score to join
+//                 the two halves, softmax over <= 16 scores in registers, then accumulates its 32 output dims.
+//   frames <= 32: lane = query frame, full 64 dims per lane (no shuffles).
+// Layout [clip][frame][pixel][row stride]; output dense [.., heads*64].
 // ---------------------------------------------------------------------------------------------
-__global__ void temporal_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                                          const __nv_bfloat16* __restrict__ v, int frames, long long hw, int heads,
-                                          float scale, long long in_stride, long long total_warps,
-                                          __nv_bfloat16* __restrict__ out) {
+template <int HALVES>  // 2: two lanes per frame (frames <= 16); 1: one lane per frame (frames <= 32)
+__global__ void __launch_bounds__(128)
+temporal_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                          const __nv_bfloat16* __restrict__ v, int frames, long long hw, int heads, float scale,
+                          long long in_stride, long long total_warps, __nv_bfloat16* __restrict__ out) {
+  constexpr int D = 64 / HALVES;        // head-dim elements owned by a lane
+  constexpr int MAXF = 32 / HALVES;     // max frames
   const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   if (wid >= total_warps) return;
   const int lane = threadIdx.x & 31;
@@ -447,54 +454,103 @@ __global__ void temporal_attention_kernel(const __nv_bfloat16* __restrict__ q, c
   const long long cstride = static_cast<long long>(heads) * 64;
   const long long fstride = hw * in_stride;   // input frame stride (rows may be views of a fused QKV buffer)
   const long long ofstride = hw * cstride;    // output is dense
-  const long long base = (clip * frames * hw + pix) * in_stride + head * 64 + lane * 2;
-  const long long obase = (clip * frames * hw + pix) * cstride + head * 64 + lane * 2;
-  float2 kf[32], vf[32];
+  const int fi = lane / HALVES;               // query frame of this lane
+  const int half = lane % HALVES;
+  const bool active = fi < frames;
+  const long long base = (clip * frames * hw + pix) * in_stride + head * 64 + half * D;
+  const long long obase = (clip * frames * hw + pix) * cstride + head * 64 + half * D;
+  float qf[D];
+  {
+    const int fq = active ? fi : 0;
+    const uint4* qp = reinterpret_cast<const uint4*>(q + base + fq * fstride);
 #pragma unroll
-  for (int f = 0; f < 32; ++f) {
-    if (f < frames) {
-      kf[f] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(k + base + f * fstride));
-      vf[f] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + base + f * fstride));
+    for (int u = 0; u < D / 8; ++u) {
+      const uint4 w = __ldg(qp + u);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h2[e]);
+        qf[u * 8 + 2 * e] = f.x * scale;
+        qf[u * 8 + 2 * e + 1] = f.y * scale;
+      }
     }
   }
-  for (int i = 0; i < frames; ++i) {
-    const float2 qf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(q + base + i * fstride));
-    float s[32];
-    float mx = -INFINITY;
+  float s[MAXF];
+  float mx = -INFINITY;
 #pragma unroll
-    for (int f = 0; f < 32; ++f) {
-      if (f < frames) {
-        float d = qf.x * kf[f].x + qf.y * kf[f].y;
+  for (int j = 0; j < MAXF; ++j) {
+    s[j] = -INFINITY;
+    if (j < frames) {
+      const uint4* kp = reinterpret_cast<const uint4*>(k + base + j * fstride);
+      float d = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        s[f] = d * scale;
-        mx = fmaxf(mx, s[f]);
+      for (int u = 0; u < D / 8; ++u) {
+        const uint4 w = __ldg(kp + u);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h2[e]);
+          d = fmaf(qf[u * 8 + 2 * e], f.x, d);
+          d = fmaf(qf[u * 8 + 2 * e + 1], f.y, d);
+        }
+      }
+      if (HALVES == 2) d += __shfl_xor_sync(0xffffffffu, d, 1);
+      s[j] = d;
+      mx = fmaxf(mx, d);
+    }
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXF; ++j) {
+    if (j < frames) {
+      const float pe = __expf(s[j] - mx);
+      l += pe;
+      s[j] = round_bf16(pe);  // P is bf16 in the fused SDPA kernels of the reference path
+    }
+  }
+  float o[D];
+#pragma unroll
+  for (int e = 0; e < D; ++e) o[e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXF; ++j) {
+    if (j < frames) {
+      const uint4* vp = reinterpret_cast<const uint4*>(v + base + j * fstride);
+      const float pj = s[j];
+#pragma unroll
+      for (int u = 0; u < D / 8; ++u) {
+        const uint4 w = __ldg(vp + u);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h2[e]);
+          o[u * 8 + 2 * e] = fmaf(pj, f.x, o[u * 8 + 2 * e]);
+          o[u * 8 + 2 * e + 1] = fmaf(pj, f.y, o[u * 8 + 2 * e + 1]);
+        }
       }
     }
-    float l = 0.f, ox = 0.f, oy = 0.f;
-#pragma unroll
-    for (int f = 0; f < 32; ++f) {
-      if (f < frames) {
-        const float p = __expf(s[f] - mx);
-        l += p;
-        const float pb = round_bf16(p);  // P is bf16 in the fused SDPA kernels of the reference path
-        ox += pb * vf[f].x;
-        oy += pb * vf[f].y;
-      }
-    }
+  }
+  if (active) {
     const float inv = 1.0f / l;
-    *reinterpret_cast<__nv_bfloat162*>(out + obase + i * ofstride) = __floats2bfloat162_rn(ox * inv, oy * inv);
+    uint4* op = reinterpret_cast<uint4*>(out + obase + fi * ofstride);
+#pragma unroll
+    for (int u = 0; u < D / 8; ++u)
+      op[u] = make_uint4(pack_bf16x2(o[u * 8] * inv, o[u * 8 + 1] * inv), pack_bf16x2(o[u * 8 + 2] * inv, o[u * 8 + 3] * inv),
+                         pack_bf16x2(o[u * 8 + 4] * inv, o[u * 8 + 5] * inv), pack_bf16x2(o[u * 8 + 6] * inv, o[u * 8 + 7] * inv));
   }
 }
 cudaError_t launch_temporal_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int clips,
                                       int frames, long long hw, int heads, float scale, long long in_row_stride,
                                       __nv_bfloat16* out, cudaStream_t stream) {
-  if (frames > 32 || frames < 1) return cudaErrorInvalidValue;
+  if (frames > 32 || frames < 1 || (in_row_stride & 7) != 0) return cudaErrorInvalidValue;
   const long long total_warps = static_cast<long long>(clips) * hw * heads;
   const int threads = 128;
   const long long blocks = (total_warps * 32 + threads - 1) / threads;
-  temporal_attention_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(q, k, v, frames, hw, heads, scale,
-                                                                                  in_row_stride, total_warps, out);
+  if (frames <= 16)
+    temporal_attention_kernel<2><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(q, k, v, frames, hw, heads, scale,
+                                                                                       in_row_stride, total_warps, out);
+  else
+    temporal_attention_kernel<1><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(q, k, v, frames, hw, heads, scale,
+                                                                                       in_row_stride, total_warps, out);
   return cudaGetLastError();
 }
 
