@@ -48,6 +48,8 @@ def parse():
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     p.add_argument("--skip-cpu-baseline", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
+    p.add_argument("--eager-baseline", action="store_true",
+                   help="also time the oracle (restated reference) as eager bf16-autocast PyTorch on this GPU")
     p.add_argument("--skip-profile", action="store_true", help="skip the per-kernel CUDA-event profile (roofline block)")
     p.add_argument("--cpu-frame-samples", type=int, default=1, help="frame-samples (of 16) timed by the CPU legs")
     return p.parse_args()
@@ -296,8 +298,8 @@ def main():
     for i in range(a.steps):
         stepfn((a.warmup + i) % 50)
     if dist:  # the single collective of the job: gather every rank's final latents (C1 in SURVEY.md)
-        gathered = torch.empty((world,) + tuple(loop.latents.shape), device=dev, dtype=loop.latents.dtype)
-        dist.all_gather_into_tensor(gathered, loop.latents)
+        from ctrl_adapter_b200.distributed import gather_latents
+        gathered = gather_latents(loop.latents, loop.latents.shape[0] * world)
     ev1.record()
     torch.cuda.synchronize()
     if dist:
@@ -381,6 +383,50 @@ def main():
                         "unit": "GB/s", "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None,
                         "how": f"algorithmic bytes / CUDA-event time of one step; peak {peak_src}"}
 
+    eager_gpu = None
+    if a.eager_baseline and rank == 0 and a.workload == "sdxl":
+        # "reference single-GPU eager PyTorch" (BASELINE.md section 3): oracle modules, bf16 params, torch.autocast,
+        # default SDPA backend, no compile, same synthetic tensors and batch
+        try:
+            del loop
+            torch.cuda.empty_cache()
+            from oracle.adapter import ControlNetAdapter as OA
+            from oracle.cases import ADAPTER_SDXL_KW, CONTROLNET_KW
+            from oracle.controlnet import ControlNetModel as OC
+            from oracle.pipeline_sdxl import EulerDiscreteScheduler, sdxl_step
+            from oracle.unet_sdxl import UNet2DConditionModel as OU
+            with torch.device(dev):
+                ocn, oad, oun = OC(**CONTROLNET_KW), OA(**ADAPTER_SDXL_KW), OU()
+            ocn, oad, oun = (m.to(BF16).eval() for m in (ocn, oad, oun))
+            sch = EulerDiscreteScheduler()
+            sch.set_timesteps(50, device=dev)
+            ei = {k: (v.to(BF16) if v.is_floating_point() else v) for k, v in inp.items()}
+            lat = ei["latents"] * sch.init_noise_sigma
+
+            def estep(i, lat):
+                with torch.no_grad(), torch.autocast("cuda", dtype=BF16):
+                    return sdxl_step(ocn, oad, oun, sch, i, lat, ei["prompt_embeds"], ei["add_text_embeds"],
+                                     ei["add_time_ids"], ei["controlnet_prompt_embeds"], ei["control_images"])
+            for i in range(2):
+                lat = estep(i, lat)
+            torch.cuda.synchronize()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ne = 5
+            q0.record()
+            for i in range(ne):
+                lat = estep(2 + i, lat)
+            q1.record()
+            torch.cuda.synchronize()
+            ems = q0.elapsed_time(q1) / ne
+            eager_gpu = {"value": 1000.0 / ems, "unit": "steps/s", "ms_per_step": ems, "steps": ne,
+                         "what": "oracle restatement of the reference loop, eager PyTorch bf16 autocast on this GPU "
+                                 "(cuDNN / cuBLAS / SDPA), same batch and shapes"}
+            del ocn, oad, oun
+            torch.cuda.empty_cache()
+        except Exception as e:
+            eager_gpu = {"value": None, "error": repr(e)[:300]}
+        loop = None
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.skip_cpu_baseline and a.workload == "sdxl":
         try:
@@ -406,7 +452,7 @@ def main():
                        "step_frac_of_sustained_peak": round(step_tflop / (ms_step / 1000.0) / peaks["bf16_tflops_sustained"], 4)},
             "finite_outputs": finite, "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
             "launches_per_step": launches_per_step, "roofline": roofline, "kernel_families": families,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "eager_gpu_baseline": eager_gpu,
         }
         print(json.dumps(line), flush=True)
     if dist:

@@ -87,7 +87,7 @@ def _oracle_runs(make_oracle, seed, inputs, call):
     from oracle.weights import seeded_init_
     with torch.device("cuda"):
         m = make_oracle()
-    m = seeded_init_(m, seed).eval()
+    m = seeded_init_(m.cuda(), seed).eval()  # .cuda(): legacy torch.Tensor([..]) parameters ignore the device context
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     for p in m.parameters():
         p.data = _q(p.data)
@@ -118,7 +118,7 @@ def check_adapter(kind="sdxl", n=2, r=8, frames=4):
     with torch.device("cuda"):
         ours_m = ControlNetAdapter(**kw)
     ours_m.load_state_dict(sd)
-    ours_m = ours_m.to(BF16).eval()
+    ours_m = ours_m.to(BF16).cuda().eval()
     ours = ours_m(**inp16)
     torch.cuda.synchronize()
     # unselected blocks must come back as zero tensors of the input's shape, mid None for SDXL
@@ -135,7 +135,7 @@ def check_controlnet(n=2, r=8, skip_conv_in=False, scale=1.0):
     with torch.device("cuda"):
         ours_m = ControlNetModel(**cases.CONTROLNET_KW)
     ours_m.load_state_dict(sd)
-    ours_m = ours_m.to(BF16).eval()
+    ours_m = ours_m.to(BF16).cuda().eval()
     ours = ours_m(**inp16)
     torch.cuda.synchronize()
     return _compare(f"ControlNetModel n={n} r={r} skip_conv_in={int(skip_conv_in)} scale={scale}", ours, ref, eager)
@@ -151,7 +151,7 @@ def check_unet_sdxl(n=2, r=16, with_residuals=True):
     with torch.device("cuda"):
         ours_m = UNet2DConditionModel()
     ours_m.load_state_dict(sd)
-    ours_m = ours_m.to(BF16).eval()
+    ours_m = ours_m.to(BF16).cuda().eval()
     ours = ours_m(**inp16)
     torch.cuda.synchronize()
     return _compare(f"UNet2DConditionModel[sdxl] n={n} r={r} residuals={int(with_residuals)}", ours, ref, eager,
@@ -184,7 +184,7 @@ def check_unet_i2vgen(b=1, f=4, r=32, with_residuals=True):
     with torch.device("cuda"):
         ours_m = I2VGenXLUNet()
     ours_m.load_state_dict(sd)
-    ours_m = ours_m.to(BF16).eval()
+    ours_m = ours_m.to(BF16).cuda().eval()
     ours = ours_m(**inp16)
     torch.cuda.synchronize()
     return _compare(f"I2VGenXLUNet b={b} f={f} r={r} residuals={int(with_residuals)}", ours, ref, eager,
@@ -197,7 +197,8 @@ def _build_pair(make_oracle, make_ours, seed):
     with torch.device("cuda"):
         o = make_oracle()
         m = make_ours()
-    o = seeded_init_(o, seed).eval()
+    o = seeded_init_(o.cuda(), seed).eval()
+    m = m.cuda()
     m.load_state_dict(o.state_dict())
     for p_ in o.parameters():
         p_.data = _q(p_.data)
