@@ -1,16 +1,17 @@
-// Fused softmax(Q K^T * scale) V for the spatial self / cross attention of the adapter, the
-// ControlNet and the UNets.  tcgen05 MMAs with TMEM accumulators, TMA-fed 128B-swizzled
-// shared memory, online softmax in registers.
+// Fused softmax(Q K^T * scale) V for the spatial self / cross attention of the adapter, the ControlNet and the
+// UNets.  tcgen05 MMAs with TMEM accumulators, TMA-fed 128B-swizzled shared memory, online softmax in registers.
 //
 // One CTA = 128 query rows of one (batch, head) and one 64-wide slice of the value head dim.
 //   warp 0     : TMA producer (Q once, then K/V tiles of 128 keys through a 2-stage ring)
 //   warp 1     : MMA issuer + TMEM allocator.  S = Q K^T (M128 N128, K = 64*DQ) into TMEM cols [0,128);
-//                O_part = P V (M128 N64 K128, V consumed MN-major) into TMEM cols [128,192)
-//   warps 2..5 : softmax, one thread per query row: pass 1 row max, pass 2 exp2 / row sum / P -> bf16 ->
-//                swizzled smem (A operand of the PV MMA); O is accumulated in registers with the usual
-//                running-max rescale; final 1/l normalisation and 128 B row store.
-// With head dim 64 the CTA uses 112 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's
-// softmax overlaps the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3.
+//                O += P V (M128 N64 K128, V consumed MN-major) ACCUMULATED in TMEM cols [128,192)
+//   warps 2..5 : softmax, one thread per query row.  Per KV tile the 128 scores of the row are read from TMEM ONCE
+//                (4 tcgen05.ld, one wait -- the wait is the expensive part) and the S buffer is released immediately so
+//                the next tile's QK^T overlaps this tile's softmax.  The running max is "lazy": O (in TMEM) and the row
+//                sum are rescaled only when a row's max grew by more than 2^8 since the max in use (exact: softmax is
+//                shift invariant and exp2 arguments stay <= 8), so the common path never touches O.
+// With head dim 64 the CTA uses 113 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's softmax overlaps
+// the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3 (one CTA per SM).
 #include <type_traits>
 
 #include "common.cuh"
@@ -22,6 +23,7 @@ static constexpr int kAttnThreads = 192;
 static constexpr int kTileQ = 128;
 static constexpr int kTileKV = 128;
 static constexpr uint32_t kChunkBytes = 128 * 64 * 2;  // one [128 rows x 64 cols] bf16 swizzle tile = 16 KB
+static constexpr float kRescaleThreshold = 8.0f;       // log2 units
 
 template <int DQ>
 struct AttnCfg {
@@ -29,7 +31,7 @@ struct AttnCfg {
   static constexpr uint32_t kQBytes = DQ * kChunkBytes;
   static constexpr uint32_t kPBytes = 2 * kChunkBytes;
   static constexpr uint32_t kStageBytes = (DQ + 1) * kChunkBytes;  // K chunks + one V slice
-  // data + 1024: the slack serves both the 1024-byte alignment of the swizzled tiles and the 88 bytes of mbarriers.
+  // data + 1024: the slack serves both the 1024-byte alignment of the swizzled tiles and the mbarriers.
   // For DQ == 1 this is 115712 B, i.e. exactly two CTAs per SM: 2 x (115712 + 1024 reserved) = 233472 = 228 KB.
   static constexpr uint32_t kDataBytes = kQBytes + kPBytes + kStages * kStageBytes;
   static constexpr uint32_t kSmemBytes = kDataBytes + 1024;
@@ -63,7 +65,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* s_empty = bars + 6;
   uint64_t* p_full = bars + 7;
   uint64_t* o_full = bars + 8;
-  uint64_t* o_empty = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5;
@@ -88,7 +89,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     mbar_init(s_empty, 4);
     mbar_init(p_full, 4);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -101,6 +101,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
+      const int kvb = b / p.kv_batch_div;
       mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
       for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
       for (int j = 0; j < nkv; ++j) {
@@ -109,8 +110,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         mbar_arrive_expect_tx(&kv_full[st], Cfg::kStageBytes);
         uint8_t* dst = smem_kv + st * Cfg::kStageBytes;
         for (int c = 0; c < DQ; ++c)
-          tma_load_3d(dst + c * kChunkBytes, &tmap_k, &kv_full[st], h * dpad + c * 64, j * kTileKV, b / p.kv_batch_div);
-        tma_load_3d(dst + DQ * kChunkBytes, &tmap_v, &kv_full[st], h * dpad + vs * 64, j * kTileKV, b / p.kv_batch_div);
+          tma_load_3d(dst + c * kChunkBytes, &tmap_k, &kv_full[st], h * dpad + c * 64, j * kTileKV, kvb);
+        tma_load_3d(dst + DQ * kChunkBytes, &tmap_v, &kv_full[st], h * dpad + vs * 64, j * kTileKV, kvb);
       }
     }
   } else if (warp == 1) {
@@ -122,7 +123,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       auto issue_qk = [&](int j) {
         const int st = j & 1;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
-        mbar_wait(s_empty, (j & 1) ^ 1);  // softmax finished reading S of tile j-1
+        mbar_wait(s_empty, (j & 1) ^ 1);  // softmax has read S of tile j-1 into registers
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem_kv + st * Cfg::kStageBytes);
 #pragma unroll
@@ -141,15 +142,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_qk(j + 1);
         const int st = j & 1;
-        mbar_wait(p_full, j & 1);
-        mbar_wait(o_empty, (j & 1) ^ 1);  // softmax consumed O_part of tile j-1
+        mbar_wait(p_full, j & 1);  // P_j staged and (if it was needed) O rescaled
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * kChunkBytes + (k & 3) * 32, 16, 1024);
           const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
-          umma_bf16_ss(tmem_o, da, db, idesc_o, k != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // accumulate across KV tiles in TMEM
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
@@ -161,121 +161,110 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int r = q * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
     const float sl2 = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    float m_used = -INFINITY;  // the max (raw score units) the accumulated P / O / l are expressed against
+    float l_run = 0.f;
     uint8_t* p_row = smem_p + r * 128;
     const int sw = r & 7;
 
-    // One KV tile of the online softmax.  MASK is only instantiated for a ragged last tile, so the hot path carries
-    // no per-element predication; TMEM loads are software pipelined (chunk c+1 is in flight while chunk c is
-    // processed); the O rescale is skipped when no row of the warp raised its running max.
     auto tile_step = [&](auto mask_tag, int j, int kv_valid) {
       constexpr bool MASK = decltype(mask_tag)::value;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t sva[16], svb[16];
-      // ---- pass 1: row max (16-column chunks, next chunk in flight while the current one is reduced) ----
-      float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      tmem_ld_32x16(tmem_s + lane_sel, sva);
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_s + lane_sel + c * 32, sv[c]);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite the TMEM buffer
+      // ---- row max ----
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t(&cur)[16] = (c & 1) ? svb : sva;
-        uint32_t(&nxt)[16] = (c & 1) ? sva : svb;
-        if (c < 7) tmem_ld_32x16(tmem_s + lane_sel + (c + 1) * 16, nxt);
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float s0 = __uint_as_float(cur[i]), s1 = __uint_as_float(cur[i + 1]);
-          float s2 = __uint_as_float(cur[i + 2]), s3 = __uint_as_float(cur[i + 3]);
+        for (int i = 0; i < 32; i += 4) {
+          float s0 = __uint_as_float(sv[c][i]), s1 = __uint_as_float(sv[c][i + 1]);
+          float s2 = __uint_as_float(sv[c][i + 2]), s3 = __uint_as_float(sv[c][i + 3]);
           if (MASK) {
-            if (c * 16 + i >= kv_valid) s0 = -INFINITY;
-            if (c * 16 + i + 1 >= kv_valid) s1 = -INFINITY;
-            if (c * 16 + i + 2 >= kv_valid) s2 = -INFINITY;
-            if (c * 16 + i + 3 >= kv_valid) s3 = -INFINITY;
+            if (c * 32 + i >= kv_valid) s0 = -INFINITY;
+            if (c * 32 + i + 1 >= kv_valid) s1 = -INFINITY;
+            if (c * 32 + i + 2 >= kv_valid) s2 = -INFINITY;
+            if (c * 32 + i + 3 >= kv_valid) s3 = -INFINITY;
           }
           mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1); mx2 = fmaxf(mx2, s2); mx3 = fmaxf(mx3, s3);
         }
-        if (c < 7) tmem_ld_wait();
       }
-      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      const bool same = __all_sync(0xffffffffu, m_new == m_run);
-      const float alpha = same ? 1.0f : fast_exp2((m_run - m_new) * sl2);  // exp2(-inf) = 0 on the first tile
-      const float mneg = -m_new * sl2;
-      // P smem of tile j-1 must have been consumed by its PV MMA, whose result is folded in below
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        tc_fence_after();
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // ---- lazy rescale: only when this row's max exceeds the max in use by more than 2^8 ----
+      bool waited_o = false;
+      if (j == 0) {
+        m_used = m_tile;
+      } else {
+        const bool need = (m_tile - m_used) * sl2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(o_full, (j - 1) & 1);  // PV of tile j-1 has landed in O
+          tc_fence_after();
+          waited_o = true;
+          const float alpha = need ? fast_exp2((m_used - m_tile) * sl2) : 1.0f;
+          if (need) m_used = m_tile;
+          l_run *= alpha;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t ov[32];
+            tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32(tmem_o + lane_sel + c * 32, ov);
+          }
+          tmem_st_wait();
+        }
       }
-      // ---- pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P into the swizzled A tile ----
+      // ---- p = exp2(s*sl2 - m_used*sl2) (<= 2^8), row sum, bf16 P ----
+      const float mneg = -m_used * sl2;
       float rs0 = 0.f, rs1 = 0.f;
-      tmem_ld_32x16(tmem_s + lane_sel, sva);
-      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t(&cur)[16] = (c & 1) ? svb : sva;
-        uint32_t(&nxt)[16] = (c & 1) ? sva : svb;
-        if (c < 7) tmem_ld_32x16(tmem_s + lane_sel + (c + 1) * 16, nxt);
-        uint32_t pk[8];
+      for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(cur[i]), sl2, mneg));
-          float p1 = fast_exp2(fmaf(__uint_as_float(cur[i + 1]), sl2, mneg));
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), sl2, mneg));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), sl2, mneg));
           if (MASK) {
-            if (c * 16 + i >= kv_valid) p0 = 0.f;
-            if (c * 16 + i + 1 >= kv_valid) p1 = 0.f;
+            if (c * 32 + i >= kv_valid) p0 = 0.f;
+            if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
           }
           rs0 += p0;
           rs1 += p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+          sv[c][i >> 1] = pack_bf16x2(p0, p1);  // packed P overwrites the already consumed scores in place
         }
-        uint8_t* chunk = p_row + (c >> 2) * kChunkBytes;  // 64 columns (4 chunks of 16) per swizzle tile
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int unit = (c & 3) * 2 + u;  // 16-byte unit inside the 128-byte row
-          *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) =
-              make_uint4(pk[u * 4], pk[u * 4 + 1], pk[u * 4 + 2], pk[u * 4 + 3]);
-        }
-        if (c < 7) tmem_ld_wait();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-      l_run = l_run * alpha + (rs0 + rs1);
-      // ---- fold in O_part of tile j-1, then rescale to the new running max ----
-      if (j > 0) {
-        tmem_ld_32x16(tmem_o + lane_sel, sva);
-        tmem_ld_wait();
+      l_run += rs0 + rs1;
+      // P smem of tile j-1 must have been consumed by its PV MMA before it is overwritten
+      if (j > 0 && !waited_o) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+      }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t(&cur)[16] = (c & 1) ? svb : sva;
-          uint32_t(&nxt)[16] = (c & 1) ? sva : svb;
-          if (c < 3) tmem_ld_32x16(tmem_o + lane_sel + (c + 1) * 16, nxt);
-          if (same) {
+      for (int c = 0; c < 4; ++c) {
+        uint8_t* chunk = p_row + (c >> 1) * kChunkBytes;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] += __uint_as_float(cur[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o_acc[c * 16 + i] = (o_acc[c * 16 + i] + __uint_as_float(cur[i])) * alpha;
-          }
-          if (c < 3) tmem_ld_wait();
+        for (int u = 0; u < 4; ++u) {
+          const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 128-byte row
+          *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) =
+              make_uint4(sv[c][u * 4], sv[c][u * 4 + 1], sv[c][u * 4 + 2], sv[c][u * 4 + 3]);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
       }
       fence_proxy_async_smem();  // P stores -> visible to the tensor core (async proxy)
+      tc_fence_before();         // orders the tcgen05.st of a rescale before the MMA that follows the barrier
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      m_run = m_new;
     };
     for (int j = 0; j < nkv; ++j) {
       const int kv_valid = min(kTileKV, p.lk - j * kTileKV);
       if (kv_valid == kTileKV) tile_step(std::false_type{}, j, kv_valid);
       else tile_step(std::true_type{}, j, kv_valid);
     }
-    // last PV
+    // epilogue: O / l
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
@@ -283,17 +272,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_batch_stride +
                           static_cast<long long>(row) * p.out_row_stride + h * dpad + vs * 64;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t ov[16];
-      tmem_ld_32x16(tmem_o + lane_sel + c * 16, ov);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
       tmem_ld_wait();
       if (row < p.lq) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = (o_acc[c * 16 + u * 8 + e] + __uint_as_float(ov[u * 8 + e])) * inv_l;
-          *reinterpret_cast<uint4*>(orow + c * 16 + u * 8) = make_uint4(
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(ov[u * 8 + e]) * inv_l;
+          *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = make_uint4(
               pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         }
       }
