@@ -106,7 +106,8 @@ def load():
         raise CtrlAdapterB200Error(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU / PyTorch fallback for the hot path)")
-    lib = C.CDLL(LIB_PATH)
+    # CA_B200_LIB: developer override (e.g. the -DCA_TRACE build made by scripts/gemm_trace.py)
+    lib = C.CDLL(os.environ.get("CA_B200_LIB", LIB_PATH))
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.argtypes = argtypes

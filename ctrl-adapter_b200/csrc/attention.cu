@@ -102,17 +102,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       const int kvb = b / p.kv_batch_div;
+      TR_DECL(tr_kv_empty);
       mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
       for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        TR_WAIT(tr_kv_empty, mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1));
         mbar_arrive_expect_tx(&kv_full[st], Cfg::kStageBytes);
         uint8_t* dst = smem_kv + st * Cfg::kStageBytes;
         for (int c = 0; c < DQ; ++c)
           tma_load_3d(dst + c * kChunkBytes, &tmap_k, &kv_full[st], h * dpad + c * 64, j * kTileKV, kvb);
         tma_load_3d(dst + DQ * kChunkBytes, &tmap_v, &kv_full[st], h * dpad + vs * 64, j * kTileKV, kvb);
       }
+      TR_PUT(9, tr_kv_empty);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -120,10 +122,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V tile) is MN-major
       const uint32_t q_addr = smem_u32(smem_q);
       const uint32_t p_addr = smem_u32(smem_p);
+      TR_DECL(tr_kv_full);
+      TR_DECL(tr_s_empty);
+      TR_DECL(tr_p_full);
+      [[maybe_unused]] const long long tr_start = TR_NOW();
       auto issue_qk = [&](int j) {
         const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
-        mbar_wait(s_empty, (j & 1) ^ 1);  // softmax has read S of tile j-1 into registers
+        TR_WAIT(tr_kv_full, mbar_wait(&kv_full[st], (j >> 1) & 1));
+        TR_WAIT(tr_s_empty, mbar_wait(s_empty, (j & 1) ^ 1));  // softmax has read S of tile j-1 into registers
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem_kv + st * Cfg::kStageBytes);
 #pragma unroll
@@ -142,7 +148,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_qk(j + 1);
         const int st = j & 1;
-        mbar_wait(p_full, j & 1);  // P_j staged and (if it was needed) O rescaled
+        TR_WAIT(tr_p_full, mbar_wait(p_full, j & 1));  // P_j staged and (if it was needed) O rescaled
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes);
 #pragma unroll
@@ -154,6 +160,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
       }
+      TR_PUT(5, tr_kv_full);
+      TR_PUT(6, tr_s_empty);
+      TR_PUT(7, tr_p_full);
+      TR_PUT(8, TR_NOW() - tr_start);
     }
   } else {
     // ===================== softmax / output: one thread per query row =====================
@@ -165,15 +175,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     float l_run = 0.f;
     uint8_t* p_row = smem_p + r * 128;
     const int sw = r & 7;
+    TR_DECL(tr_s_full);
+    TR_DECL(tr_o_full);
+    TR_DECL(tr_ld);
+    TR_DECL(tr_resc);
+    [[maybe_unused]] const long long tr_start = TR_NOW();
 
     auto tile_step = [&](auto mask_tag, int j, int kv_valid) {
       constexpr bool MASK = decltype(mask_tag)::value;
-      mbar_wait(s_full, j & 1);
+      TR_WAIT(tr_s_full, mbar_wait(s_full, j & 1));
       tc_fence_after();
       uint32_t sv[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_s + lane_sel + c * 32, sv[c]);
-      tmem_ld_wait();
+      TR_WAIT(tr_ld, tmem_ld_wait());
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite the TMEM buffer
@@ -202,6 +217,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       } else {
         const bool need = (m_tile - m_used) * sl2 > kRescaleThreshold;
         if (__any_sync(0xffffffffu, need)) {
+#ifdef CA_TRACE
+          ++tr_resc;
+#endif
           mbar_wait(o_full, (j - 1) & 1);  // PV of tile j-1 has landed in O
           tc_fence_after();
           waited_o = true;
@@ -241,7 +259,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       l_run += rs0 + rs1;
       // P smem of tile j-1 must have been consumed by its PV MMA before it is overwritten
       if (j > 0 && !waited_o) {
-        mbar_wait(o_full, (j - 1) & 1);
+        TR_WAIT(tr_o_full, mbar_wait(o_full, (j - 1) & 1));
         tc_fence_after();
       }
 #pragma unroll
@@ -263,6 +281,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       const int kv_valid = min(kTileKV, p.lk - j * kTileKV);
       if (kv_valid == kTileKV) tile_step(std::false_type{}, j, kv_valid);
       else tile_step(std::true_type{}, j, kv_valid);
+    }
+    if (warp == 2 && lane == 0) {
+      TR_PUT(0, TR_NOW() - tr_start);
+      TR_PUT(1, tr_s_full);
+      TR_PUT(2, tr_o_full);
+      TR_PUT(3, tr_resc);
+      TR_PUT(4, tr_ld);
     }
     // epilogue: O / l
     mbar_wait(o_full, (nkv - 1) & 1);

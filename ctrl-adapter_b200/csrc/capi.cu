@@ -83,6 +83,13 @@ int num_sms() {
     return CA_OK;                                  \
   } while (0)
 
+// developer instrumentation (only read by -DCA_TRACE builds): device buffer of 16 u64 counters per CTA
+unsigned long long* trace_ptr() {
+  static const char* env = getenv("CA_GEMM_TRACE_PTR");
+  static unsigned long long* ptr = env ? reinterpret_cast<unsigned long long*>(strtoull(env, nullptr, 0)) : nullptr;
+  return ptr;
+}
+
 }  // namespace
 
 extern "C" {
@@ -168,6 +175,7 @@ int ca_gemm(const ca_gemm_desc* d, void* cuda_stream) {
   p.blend_alpha = d->blend_alpha;
   if (p.blend_src && !p.blend_alpha) return fail(CA_ERR_INVALID, "blend_src without blend_alpha");
   p.out = d->out;
+  p.trace = trace_ptr();
 
   CUtensorMap ta[2], tw;
   memset(ta, 0, sizeof(ta));
@@ -231,6 +239,7 @@ int ca_attention(const ca_attention_desc* d, void* cuda_stream) {
   ca::AttnParams p;
   p.batch = d->batch; p.heads = d->heads; p.lq = d->lq; p.lk = d->lk;
   p.kv_batch_div = kv_div;
+  p.trace = trace_ptr();
   p.dqk_chunks = d->head_dim_pad / 64;
   p.v_slices = d->head_dim_pad / 64;
   p.scale_log2 = d->scale * 1.4426950408889634f;

@@ -34,6 +34,21 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// packed bf16 arithmetic with ONE rounding of the exact result -- identical to PyTorch's bf16 add / mul
+// (fp32 op on the widened operands, then round-to-nearest-even), at half the instructions of unpack / op / repack
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ float bf16lo_to_float(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_to_float(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -203,7 +218,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 // arrive on the mbarrier at the same offset in the leader CTA of the pair (works from either CTA)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+  // .relaxed: a .release at cluster scope is compiled to MEMBAR.ALL.GPU, which stalls the arriving warp until all of
+  // its global stores have been acknowledged (2-3k cycles per tile in the GEMM epilogue).  The only thing ordered
+  // through these barriers is TMEM traffic, which tcgen05.wait + tcgen05.fence::before_thread_sync already order.
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
                : "memory");
 }
 // TMA loads issued by either CTA of a pair; completion bytes are credited to the LEADER's mbarrier
@@ -286,3 +304,18 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
 }
 
 }  // namespace ca
+
+// Developer instrumentation (scripts/gemm_trace.py): cycles each role of a kernel spends blocked, 16 counters per CTA
+// written through the `trace` pointer of the kernel's Params struct.  Compiled out unless -DCA_TRACE.
+#ifdef CA_TRACE
+#define TR_CTA() (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z))
+#define TR_DECL(v_) long long v_ = 0
+#define TR_WAIT(v_, stmt) do { const long long _t0 = clock64(); stmt; v_ += clock64() - _t0; } while (0)
+#define TR_PUT(slot, v_) do { if (p.trace != nullptr && TR_CTA() < 4096) p.trace[TR_CTA() * 16 + (slot)] = static_cast<unsigned long long>(v_); } while (0)
+#define TR_NOW() clock64()
+#else
+#define TR_DECL(v_)
+#define TR_WAIT(v_, stmt) stmt
+#define TR_PUT(slot, v_)
+#define TR_NOW() 0
+#endif

@@ -34,6 +34,7 @@ struct GemmParams {
   const __nv_bfloat16* blend_src;  // AlphaBlender x_spatial, indexed through rstride
   const float* blend_alpha;        // device scalar: sigmoid(mix_factor), bf16-valued
   void* out;
+  unsigned long long* trace;  // developer builds (-DCA_TRACE) only: per-CTA role wait-cycle counters, else unused
 };
 
 cudaError_t launch_gemm_conv(int bn, int ncta, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
@@ -47,6 +48,7 @@ struct AttnParams {
   float scale_log2;    // softmax scale * log2(e)
   __nv_bfloat16* out;  // [batch, lq, heads * 64 * v_slices]
   long long out_batch_stride, out_row_stride;  // elements
+  unsigned long long* trace;  // -DCA_TRACE builds only
 };
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream);

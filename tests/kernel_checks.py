@@ -213,7 +213,11 @@ def check_attention(b, heads, lq, lk, d, seed=0, ramp=0.0):
     out = ops.attention(pad(q), pad(k), pad(v), heads, dp, scale)
     torch.cuda.synchronize()
     out = out.reshape(b, lq, heads, dp)[..., :d]
-    rec = _report(f"attention b{b} h{heads} lq{lq} lk{lk} d{d}" + (f" ramp{ramp:g}" if ramp else ""), out, ref, 2e-2, 2e-3, {"sdpa_bf16_max_err": sd_err})
+    # ramped logits give nearly one-hot rows: the output is a bf16-rounded V row (|v| up to ~4.6, half-ulp 9e-3), so the
+    # absolute floor follows torch's own bf16 SDPA error instead of the iid-case 2e-3
+    atol = 2e-3 if not ramp else max(2e-3, 1.25 * sd_err)
+    rec = _report(f"attention b{b} h{heads} lq{lq} lk{lk} d{d}" + (f" ramp{ramp:g}" if ramp else ""), out, ref, 2e-2, atol,
+                  {"sdpa_bf16_max_err": sd_err})
     if rec["max_abs_err"] > 2.0 * sd_err + 1e-3:
         rec["ok"] = False
         rec["why"] = "error larger than 2x torch bf16 SDPA"
@@ -398,6 +402,13 @@ def run_all(stop_on_fail=False, group=None):
         lambda: check_linear_rowvec(1024, 512, 512, 256),
         lambda: check_linear_rowvec(192, 320, 320, 64),
         lambda: check_linear_blend(512, 2048, 512),
+        # lean epilogue specialisations (bias / bias+residual / GEGLU) over every BN and ragged edges
+        lambda: check_linear(3000, 640, 640, out_fp32=False, residual=True),       # BN 160: 80-column warp shares
+        lambda: check_linear(1100, 320, 1920, out_fp32=False),                      # BN 128, partial last M tile
+        lambda: check_linear(2048, 1280, 1280, out_fp32=False, residual=True),      # BN 256, two units per warp
+        lambda: check_linear(700, 256, 328, out_fp32=False, residual=True),         # n_out not a multiple of 64
+        lambda: check_linear(520, 192, 40, out_fp32=False, bias=False),             # BN 64, single partial unit
+        lambda: check_geglu(5000, 640, 2560),
         lambda: check_conv(2, 16, 16, 64, 64),
         lambda: check_conv(2, 32, 32, 320, 320),
         lambda: check_conv(3, 8, 8, 1280, 1280, out_fp32=False, rowvec=True, residual=True),
@@ -437,7 +448,7 @@ def run_all(stop_on_fail=False, group=None):
         check_router,
         check_cfg,
     ]
-    groups = {"gemm": (0, 12), "conv": (12, 26), "attn": (26, 36), "misc": (36, len(plan))}
+    groups = {"gemm": (0, 18), "conv": (18, 32), "attn": (32, 45), "misc": (45, len(plan))}
     if group:
         lo, hi = groups[group]
         plan = plan[lo:hi]
