@@ -1,15 +1,23 @@
 // Fused softmax(Q K^T * scale) V for the spatial self / cross attention of the adapter, the ControlNet and the
 // UNets.  tcgen05 MMAs with TMEM accumulators, TMA-fed 128B-swizzled shared memory, online softmax in registers.
 //
-// One CTA = 128 query rows of one (batch, head) and one 64-wide slice of the value head dim.
-//   warp 0     : TMA producer (Q once, then K/V tiles of 128 keys through a 2-stage ring)
-//   warp 1     : MMA issuer + TMEM allocator.  S = Q K^T (M128 N128, K = 64*DQ) into TMEM cols [0,128);
-//                O += P V (M128 N64 K128, V consumed MN-major) ACCUMULATED in TMEM cols [128,192)
-//   warps 2..5 : softmax, one thread per query row.  Per KV tile the 128 scores of the row are read from TMEM ONCE
-//                (4 tcgen05.ld, one wait -- the wait is the expensive part) and the S buffer is released immediately so
-//                the next tile's QK^T overlaps this tile's softmax.  The running max is "lazy": O (in TMEM) and the row
-//                sum are rescaled only when a row's max grew by more than 2^8 since the max in use (exact: softmax is
-//                shift invariant and exp2 arguments stay <= 8), so the common path never touches O.
+// One CTA = 128 query rows of one (batch, head) and one 64-wide slice of the value head dim; 256 threads:
+//   warpgroup 0: warp 0 = TMA producer (Q once, then K/V tiles of 128 keys through a 2-stage ring),
+//                warp 1 = MMA issuer + TMEM allocator.  S = Q K^T (M128 N128, K = 64*DQ) into TMEM cols [0,128);
+//                O += P V (M128 N64 K128, V consumed MN-major) ACCUMULATED in TMEM cols [128,192).  Warps 2-3 idle.
+//   warpgroup 1: softmax, one thread per query row.  Per KV tile the 128 scores of the row are read from TMEM ONCE
+//                (4 tcgen05.ld, one wait) and the S buffer is released immediately so the next tile's QK^T overlaps
+//                this tile's softmax.  The running max is "lazy": O (in TMEM) and the row sum are rescaled only when a
+//                row's max grew by more than 2^8 since the max in use (exact: softmax is shift invariant and exp2
+//                arguments stay <= 8), so the common path never touches O.
+// The softmax warps are the bottleneck (the tensor pipe idles ~70%), so their instruction stream is what is optimised:
+//   * packed fp32x2 FFMA2 / FADD2 for the scale-and-shift and the row sum;
+//   * MUFU.EX2 (16 / clk / SM) is the scarcest pipe: a compile-time share of the exponentials (kPolyOf8 pairs out of
+//     8) is evaluated on the FMA pipe instead -- Cody-Waite split, cubic minimax 2^f on [-0.5, 0.5] (7.5e-5 relative,
+//     1/26 of a bf16 half-ulp of P), exponent spliced in with an integer add;
+//   * setmaxnreg moves registers from warpgroup 0 (24 each) to the softmax warpgroup (232 each) so the 128 scores of
+//     a row stay in registers without spills while two CTAs still share an SM;
+//   * the producer / MMA warps back off with nanosleep while blocked so their polling does not steal issue slots.
 // With head dim 64 the CTA uses 113 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's softmax overlaps
 // the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3 (one CTA per SM).
 #include <type_traits>
@@ -19,7 +27,8 @@
 
 namespace ca {
 
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 256;
+static constexpr int kPolyOf8 = 2;  // pairs out of every 8 whose exp2 runs on the FMA pipe instead of MUFU
 static constexpr int kTileQ = 128;
 static constexpr int kTileKV = 128;
 static constexpr uint32_t kChunkBytes = 128 * 64 * 2;  // one [128 rows x 64 cols] bf16 swizzle tile = 16 KB
@@ -42,6 +51,55 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2: two lanes per issued instruction) ----
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a pair on the FMA / ALU pipes only.  x <= 8 by construction; clamped below so the exponent splice cannot wrap
+// (anything under 2^-100 is irrelevant next to a row sum >= 2^-8).
+__device__ __forceinline__ void exp2_poly_x2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t x = pack_f32x2(fmaxf(x0, -100.0f), fmaxf(x1, -100.0f));
+  const uint64_t t = add_f32x2(x, pack_f32x2(12582912.0f, 12582912.0f));          // round(x) lands in the mantissa
+  const uint64_t r = add_f32x2(t, pack_f32x2(-12582912.0f, -12582912.0f));         // round(x) as a float
+  const uint64_t f = fma_f32x2(r, pack_f32x2(-1.0f, -1.0f), x);                     // x - round(x) in [-0.5, 0.5]
+  uint64_t p = fma_f32x2(pack_f32x2(0.0551716685f, 0.0551716685f), f, pack_f32x2(0.2426111251f, 0.2426111251f));
+  p = fma_f32x2(p, f, pack_f32x2(0.6932609677f, 0.6932609677f));
+  p = fma_f32x2(p, f, pack_f32x2(0.9999280572f, 0.9999280572f));
+  float t0, t1, q0, q1;
+  unpack_f32x2(t, t0, t1);
+  unpack_f32x2(p, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+__host__ __device__ constexpr bool pair_uses_poly(int pair) {  // kPolyOf8 of every 8 pairs, evenly spread
+  return ((pair % 8 + 1) * kPolyOf8) / 8 != ((pair % 8) * kPolyOf8) / 8;
+}
+
+template <int R>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+
+// blocked for a long time by design (producer on a free K/V slot, MMA issuer on the softmax): poll politely
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
 template <int DQ>
@@ -99,6 +157,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
 
+  if (warp < 4) {
+    if constexpr (DQ == 1) setmaxnreg_dec<24>();
+  }
   if (warp == 0) {
     if (lane == 0) {
       const int kvb = b / p.kv_batch_div;
@@ -107,7 +168,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
-        TR_WAIT(tr_kv_empty, mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1));
+        TR_WAIT(tr_kv_empty, mbar_wait_backoff(&kv_empty[st], ((j >> 1) & 1) ^ 1));
         mbar_arrive_expect_tx(&kv_full[st], Cfg::kStageBytes);
         uint8_t* dst = smem_kv + st * Cfg::kStageBytes;
         for (int c = 0; c < DQ; ++c)
@@ -148,7 +209,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_qk(j + 1);
         const int st = j & 1;
-        TR_WAIT(tr_p_full, mbar_wait(p_full, j & 1));  // P_j staged and (if it was needed) O rescaled
+        TR_WAIT(tr_p_full, mbar_wait_backoff(p_full, j & 1));  // P_j staged and (if it was needed) O rescaled
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes);
 #pragma unroll
@@ -165,8 +226,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       TR_PUT(7, tr_p_full);
       TR_PUT(8, TR_NOW() - tr_start);
     }
-  } else {
+  } else if (warp >= 4) {
     // ===================== softmax / output: one thread per query row =====================
+    if constexpr (DQ == 1) setmaxnreg_inc<232>();
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
@@ -241,20 +303,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // ---- p = exp2(s*sl2 - m_used*sl2) (<= 2^8), row sum, bf16 P ----
       const float mneg = -m_used * sl2;
       float rs0 = 0.f, rs1 = 0.f;
+      if constexpr (MASK) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), sl2, mneg));
-          float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), sl2, mneg));
-          if (MASK) {
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), sl2, mneg));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), sl2, mneg));
             if (c * 32 + i >= kv_valid) p0 = 0.f;
             if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
+            rs0 += p0;
+            rs1 += p1;
+            sv[c][i >> 1] = pack_bf16x2(p0, p1);  // packed P overwrites the already consumed scores in place
           }
-          rs0 += p0;
-          rs1 += p1;
-          sv[c][i >> 1] = pack_bf16x2(p0, p1);  // packed P overwrites the already consumed scores in place
         }
+      } else {
+        const uint64_t sl2_2 = pack_f32x2(sl2, sl2), mneg_2 = pack_f32x2(mneg, mneg);
+        uint64_t rs_a = pack_f32x2(0.f, 0.f), rs_b = rs_a;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t x =
+                fma_f32x2(pack_f32x2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sl2_2, mneg_2);
+            float x0, x1, p0, p1;
+            unpack_f32x2(x, x0, x1);
+            if (pair_uses_poly(i >> 1)) {
+              exp2_poly_x2(x0, x1, p0, p1);
+            } else {
+              p0 = fast_exp2(x0);
+              p1 = fast_exp2(x1);
+            }
+            if ((i >> 1) & 1) rs_b = add_f32x2(rs_b, pack_f32x2(p0, p1));
+            else rs_a = add_f32x2(rs_a, pack_f32x2(p0, p1));
+            sv[c][i >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+        float a0, a1;
+        unpack_f32x2(add_f32x2(rs_a, rs_b), a0, a1);
+        rs0 = a0;
+        rs1 = a1;
       }
       l_run += rs0 + rs1;
       // P smem of tile j-1 must have been consumed by its PV MMA before it is overwritten
@@ -282,7 +370,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (kv_valid == kTileKV) tile_step(std::false_type{}, j, kv_valid);
       else tile_step(std::true_type{}, j, kv_valid);
     }
-    if (warp == 2 && lane == 0) {
+    if (warp == 4 && lane == 0) {
       TR_PUT(0, TR_NOW() - tr_start);
       TR_PUT(1, tr_s_full);
       TR_PUT(2, tr_o_full);
