@@ -51,7 +51,7 @@ def parse():
     p.add_argument("--eager-baseline", action="store_true",
                    help="also time the oracle (restated reference) as eager bf16-autocast PyTorch on this GPU")
     p.add_argument("--skip-profile", action="store_true", help="skip the per-kernel CUDA-event profile (roofline block)")
-    p.add_argument("--cpu-frame-samples", type=int, default=1, help="frame-samples (of 16) timed by the CPU legs")
+    p.add_argument("--cpu-sample-res", type=int, default=512, help="resolution of the one-frame-sample pass timed by the CPU legs")
     return p.parse_args()
 
 
@@ -118,61 +118,73 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(frame_samples, res, steps, warmup, budget_s=150.0):
-    """Oracle (restated reference PyTorch path) on the host CPU, fp32 eager, all threads.
-    Sample = `frame_samples` of the 16 frame-samples of one step: 2 -> one image with its CFG pair through the restated
-    pipeline loop body; 1 -> one frame-sample through ControlNet -> adapter -> UNet (CFG / scheduler arithmetic is
-    latent-sized and negligible).  Measured on a 128-thread Xeon: ~95 s per frame-sample, hence the small default.
-    Returns (steps_per_s normalised to the 16-frame-sample workload, info dict)."""
+def _oracle_frame_sample(cn, ad, un, inp, lat, t, res):
+    """One frame-sample through ControlNet (at res/2) -> adapter -> UNet, restated reference modules."""
+    F = torch.nn.functional
+    down, mid = cn(F.adaptive_avg_pool2d(lat, (res // 16, res // 16)), t,
+                   encoder_hidden_states=inp["controlnet_prompt_embeds"][:1],
+                   controlnet_cond=F.adaptive_avg_pool2d(inp["control_images"][:1], (res // 2, res // 2)),
+                   conditioning_scale=1.0, return_dict=False)
+    da, _ = ad(down, num_frames=1, timestep=t, encoder_hidden_states=inp["prompt_embeds"][:1])
+    un(lat, t, encoder_hidden_states=inp["prompt_embeds"][:1],
+       added_cond_kwargs={"text_embeds": inp["add_text_embeds"][:1], "time_ids": inp["add_time_ids"][:1]},
+       down_block_additional_residuals=da, mid_block_additional_residual=0)
+
+
+def _oracle_flops_per_frame_sample(res):
+    """Exact matmul / conv / attention FLOPs of one frame-sample at `res`, counted on meta tensors (no compute)."""
+    from torch.utils.flop_counter import FlopCounterMode
     from oracle.adapter import ControlNetAdapter
     from oracle.cases import ADAPTER_SDXL_KW, CONTROLNET_KW
     from oracle.controlnet import ControlNetModel
-    from oracle.pipeline_sdxl import EulerDiscreteScheduler, sdxl_step
     from oracle.unet_sdxl import UNet2DConditionModel
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    with torch.device("meta"):
+        cn, ad, un = ControlNetModel(**CONTROLNET_KW).eval(), ControlNetAdapter(**ADAPTER_SDXL_KW).eval(), UNet2DConditionModel().eval()
+    inp = {k: (v.to("meta") if torch.is_tensor(v) else v) for k, v in synthetic_inputs(1, res, "cpu", 1234).items()}
+    with FlopCounterMode(display=False) as fc, torch.no_grad():
+        _oracle_frame_sample(cn, ad, un, inp, inp["latents"][:1], torch.tensor(500.0), res)
+    return float(fc.get_total_flops())
+
+
+def cpu_reference_step_rate(sample_res, res, steps, warmup, budget_s=60.0):
+    """Oracle (restated reference PyTorch path) on the host CPU, fp32 eager, all threads, on a BOUNDED sample.
+    One full step (16 frame-samples at 1024x1024) takes ~45 minutes on a 128-thread Xeon, so a timed pass is ONE
+    frame-sample at `sample_res` (default 512: ~20-40 s) and the rate is scaled to the full step by the exact
+    FLOP ratio (torch FlopCounterMode on meta tensors): steps/s = 1 / (t_pass * F_step / F_pass).
+    Returns (steps_per_s of the 16-frame-sample workload at `res`, info dict)."""
+    from oracle.adapter import ControlNetAdapter
+    from oracle.cases import ADAPTER_SDXL_KW, CONTROLNET_KW
+    from oracle.controlnet import ControlNetModel
+    from oracle.pipeline_sdxl import EulerDiscreteScheduler
+    from oracle.unet_sdxl import UNet2DConditionModel
+    cores = torch.get_num_threads()  # torch's default: one thread per physical core it may use
     torch.manual_seed(0)
     t0 = time.time()
     cn = ControlNetModel(**CONTROLNET_KW).eval()
     ad = ControlNetAdapter(**ADAPTER_SDXL_KW).eval()
     un = UNet2DConditionModel().eval()
     build_s = time.time() - t0
+    f_pass = _oracle_flops_per_frame_sample(sample_res)
+    f_step = 16.0 * (f_pass if sample_res == res else _oracle_flops_per_frame_sample(res))
     sch = EulerDiscreteScheduler()
     sch.set_timesteps(50)
-    inp = synthetic_inputs(1, res, "cpu", 1234)
-    lat = inp["latents"] * sch.init_noise_sigma
-
-    def one_step(i):
-        nonlocal lat
-        with torch.no_grad():
-            if frame_samples >= 2:
-                lat = sdxl_step(cn, ad, un, sch, i % 50, lat, inp["prompt_embeds"], inp["add_text_embeds"],
-                                inp["add_time_ids"], inp["controlnet_prompt_embeds"], inp["control_images"])
-            else:
-                t = sch.timesteps[i % 50]
-                x = sch.scale_model_input(lat, i % 50)
-                down, mid = cn(torch.nn.functional.adaptive_avg_pool2d(x, (64, 64)), t,
-                               encoder_hidden_states=inp["controlnet_prompt_embeds"][:1],
-                               controlnet_cond=inp["control_images"][:1], conditioning_scale=1.0, return_dict=False)
-                da, _ = ad(down, num_frames=1, timestep=t, encoder_hidden_states=inp["prompt_embeds"][:1])
-                un(x, t, encoder_hidden_states=inp["prompt_embeds"][:1],
-                   added_cond_kwargs={"text_embeds": inp["add_text_embeds"][:1], "time_ids": inp["add_time_ids"][:1]},
-                   down_block_additional_residuals=da, mid_block_additional_residual=0)
+    inp = synthetic_inputs(1, sample_res, "cpu", 1234)
+    lat = (inp["latents"] * sch.init_noise_sigma)[:1]
 
     times, done = [], 0
     t_start = time.time()
     for i in range(warmup + steps):
         t1 = time.time()
-        one_step(i)
+        with torch.no_grad():
+            _oracle_frame_sample(cn, ad, un, inp, sch.scale_model_input(lat, i % 50), sch.timesteps[i % 50], sample_res)
         dt = time.time() - t1
         done += 1
         if i >= warmup or (time.time() - t_start > budget_s):
-            times.append(dt)  # a warm-up step is promoted to a timed one when the budget is already spent
+            times.append(dt)  # a warm-up pass is promoted to a timed one when the budget is already spent
         if time.time() - t_start > budget_s and len(times) >= 1:
             break
     ms = 1000.0 * sum(times) / len(times)
-    fs = 2 if frame_samples >= 2 else 1
-    rate = (fs / 16.0) / (ms / 1000.0)
+    rate = 1.0 / ((ms / 1000.0) * (f_step / f_pass))
     cpu_model = ""
     try:
         for line in open("/proc/cpuinfo"):
@@ -181,11 +193,14 @@ def cpu_reference_step_rate(frame_samples, res, steps, warmup, budget_s=150.0):
                 break
     except Exception:
         pass
-    info = {"value": rate, "unit": "steps/s (16-frame-sample step equivalent)", "cores": cores, "kind": "port",
-            "sample": f"{fs} of the 16 frame-samples of one step at {res}x{res}, fp32 eager, {len(times)} timed pass(es) "
-                      f"of {done} executed, {ms:.0f} ms per pass; oracle restatement of the reference path (the reference "
-                      f"itself needs diffusers, not installable here); cpu: {cpu_model}",
-            "ms_per_sample_pass": ms, "model_build_s": build_s}
+    info = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": f"one frame-sample (ControlNet -> adapter -> UNet) at {sample_res}x{sample_res}, fp32 eager, "
+                      f"{len(times)} timed pass(es) of {done} executed, {ms:.0f} ms per pass = {f_pass / 1e12:.3f} TFLOP; scaled "
+                      f"to the 16-frame-sample {res}x{res} step ({f_step / 1e12:.1f} TFLOP) by the FLOP ratio; oracle "
+                      f"restatement of the reference path (the reference itself needs diffusers, not installable here); "
+                      f"cpu: {cpu_model}",
+            "ms_per_sample_pass": ms, "sample_tflop": f_pass / 1e12, "step_tflop": f_step / 1e12,
+            "cpu_tflops": f_pass / ms / 1e9, "model_build_s": build_s}
     return rate, info
 
 
@@ -193,7 +208,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, info = cpu_reference_step_rate(a.cpu_frame_samples, a.res, a.steps, a.warmup, budget_s=200.0)
+    rate, info = cpu_reference_step_rate(a.cpu_sample_res, a.res, a.steps, a.warmup, budget_s=150.0)
     line = {"impl": "reference", "metric": "denoising steps/sec (SDXL 1024x1024 + depth ControlNet + Ctrl-Adapter, batch 8)",
             "value": rate, "unit": "steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1000.0 / rate if rate > 0 else None, "higher_is_better": True, "scaling": "weak",
@@ -367,13 +382,23 @@ def main():
                         "gbs": round(v["bytes"] / (v["ms"] * 1e6), 1) if v["ms"] > 0 and v["bytes"] else None}
                     for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        # DRAM bytes per launch of the dominant kernel: ncu dram__bytes_{read,write}.sum over every launch of one step
+        # (profiles/r1_traffic_<workload>.json, made by scripts/launch_share.py from the committed launch list)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", f"r1_traffic_{a.workload}.json")))
+            kn = {"gemm": "gemm_conv_kernel", "attention": "attention_kernel"}.get(top[0])
+            if kn in tj:
+                traffic = round(tj[kn]["dram_bytes_per_launch"], 0)
+        except Exception:
+            traffic = None
         if top[0] in ("gemm", "attention"):
             ach = top[1]["flops"] / (top[1]["ms"] * 1e9)
             peak = peaks["bf16_tflops_sustained"]
             roofline = {"kernel": {"gemm": "gemm_conv_kernel (tcgen05 multi-tap GEMM / implicit conv)",
                                    "attention": "attention_kernel (tcgen05 flash attention)"}[top[0]],
                         "bound": "tensor", "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
-                        "frac": round(ach / peak, 4), "traffic": None,
+                        "frac": round(ach / peak, 4), "traffic": traffic,
                         "how": f"sum of algorithmic FLOPs of the {top[1]['launches']} launches of one step / sum of their "
                                f"CUDA-event durations ({top[1]['ms']:.1f} ms = {100 * top[1]['ms'] / tot:.0f}% of the step); "
                                f"peak = bf16_tflops_sustained, {peak_src}"}
@@ -432,7 +457,7 @@ def main():
         try:
             del loop
             torch.cuda.empty_cache()
-            _, cpu_baseline = cpu_reference_step_rate(a.cpu_frame_samples, a.res, 1, 0, budget_s=60.0)
+            _, cpu_baseline = cpu_reference_step_rate(a.cpu_sample_res, a.res, 1, 0, budget_s=60.0)
         except Exception as e:  # the CPU leg must never hide the GPU numbers
             cpu_baseline = {"value": None, "error": repr(e)[:300]}
 

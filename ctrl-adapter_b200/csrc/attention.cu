@@ -2,7 +2,8 @@
 // UNets.  tcgen05 MMAs with TMEM accumulators, TMA-fed 128B-swizzled shared memory, online softmax in registers.
 //
 // One CTA = 128 query rows of one (batch, head) and one 64-wide slice of the value head dim; 256 threads:
-//   warpgroup 0: warp 0 = TMA producer (Q once, then K/V tiles of 128 keys through a 2-stage ring),
+//   warpgroup 0: warp 0 = TMA producer (Q once, then K and V tiles of 128 keys through SEPARATE 2-stage rings:
+//                a K slot is free as soon as its QK^T retired, so K runs two tiles ahead of the softmax),
 //                warp 1 = MMA issuer + TMEM allocator.  S = Q K^T (M128 N128, K = 64*DQ) into TMEM cols [0,128);
 //                O += P V (M128 N64 K128, V consumed MN-major) ACCUMULATED in TMEM cols [128,192).  Warps 2-3 idle.
 //   warpgroup 1: softmax, one thread per query row.  Per KV tile the 128 scores of the row are read from TMEM ONCE
@@ -20,6 +21,7 @@
 //   * the producer / MMA warps back off with nanosleep while blocked so their polling does not steal issue slots.
 // With head dim 64 the CTA uses 113 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's softmax overlaps
 // the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3 (one CTA per SM).
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -28,7 +30,7 @@
 namespace ca {
 
 static constexpr int kAttnThreads = 256;
-static constexpr int kPolyOf8 = 2;  // pairs out of every 8 whose exp2 runs on the FMA pipe instead of MUFU
+static constexpr int kPolyDefault = 2;  // pairs out of every 8 whose exp2 runs on the FMA pipe instead of MUFU
 static constexpr int kTileQ = 128;
 static constexpr int kTileKV = 128;
 static constexpr uint32_t kChunkBytes = 128 * 64 * 2;  // one [128 rows x 64 cols] bf16 swizzle tile = 16 KB
@@ -88,8 +90,9 @@ __device__ __forceinline__ void exp2_poly_x2(float x0, float x1, float& p0, floa
   p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
-__host__ __device__ constexpr bool pair_uses_poly(int pair) {  // kPolyOf8 of every 8 pairs, evenly spread
-  return ((pair % 8 + 1) * kPolyOf8) / 8 != ((pair % 8) * kPolyOf8) / 8;
+template <int POLY>
+__host__ __device__ constexpr bool pair_uses_poly(int pair) {  // POLY of every 8 pairs, evenly spread
+  return ((pair % 8 + 1) * POLY) / 8 != ((pair % 8) * POLY) / 8;
 }
 
 template <int R>
@@ -102,7 +105,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
-template <int DQ>
+template <int DQ, int POLY>
 __global__ void __launch_bounds__(kAttnThreads, (DQ == 1) ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -117,13 +120,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint8_t* smem_kv = smem_p + Cfg::kPBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 10;   // [2]
+  uint64_t* v_empty = bars + 12;  // [2]
   uint64_t* s_full = bars + 5;
   uint64_t* s_empty = bars + 6;
   uint64_t* p_full = bars + 7;
   uint64_t* o_full = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,8 +145,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(s_empty, 4);
@@ -166,14 +173,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       TR_DECL(tr_kv_empty);
       mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
       for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
-      for (int j = 0; j < nkv; ++j) {
+      auto load_k = [&](int j) {
         const int st = j & 1;
-        TR_WAIT(tr_kv_empty, mbar_wait_backoff(&kv_empty[st], ((j >> 1) & 1) ^ 1));
-        mbar_arrive_expect_tx(&kv_full[st], Cfg::kStageBytes);
         uint8_t* dst = smem_kv + st * Cfg::kStageBytes;
+        TR_WAIT(tr_kv_empty, mbar_wait_backoff(&k_empty[st], ((j >> 1) & 1) ^ 1));
+        mbar_arrive_expect_tx(&k_full[st], DQ * kChunkBytes);
         for (int c = 0; c < DQ; ++c)
-          tma_load_3d(dst + c * kChunkBytes, &tmap_k, &kv_full[st], h * dpad + c * 64, j * kTileKV, kvb);
-        tma_load_3d(dst + DQ * kChunkBytes, &tmap_v, &kv_full[st], h * dpad + vs * 64, j * kTileKV, kvb);
+          tma_load_3d(dst + c * kChunkBytes, &tmap_k, &k_full[st], h * dpad + c * 64, j * kTileKV, kvb);
+      };
+      load_k(0);
+      for (int j = 0; j < nkv; ++j) {
+        // K(j+1) first: its slot frees when QK^T(j-1) retires, which precedes PV(j-2) (the condition for V(j))
+        if (j + 1 < nkv) load_k(j + 1);
+        const int st = j & 1;
+        TR_WAIT(tr_kv_empty, mbar_wait_backoff(&v_empty[st], ((j >> 1) & 1) ^ 1));
+        mbar_arrive_expect_tx(&v_full[st], kChunkBytes);
+        tma_load_3d(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes, &tmap_v, &v_full[st], h * dpad + vs * 64,
+                    j * kTileKV, kvb);
       }
       TR_PUT(9, tr_kv_empty);
     }
@@ -189,7 +205,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       [[maybe_unused]] const long long tr_start = TR_NOW();
       auto issue_qk = [&](int j) {
         const int st = j & 1;
-        TR_WAIT(tr_kv_full, mbar_wait(&kv_full[st], (j >> 1) & 1));
+        TR_WAIT(tr_kv_full, mbar_wait(&k_full[st], (j >> 1) & 1));
         TR_WAIT(tr_s_empty, mbar_wait(s_empty, (j & 1) ^ 1));  // softmax has read S of tile j-1 into registers
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem_kv + st * Cfg::kStageBytes);
@@ -203,12 +219,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
         umma_commit(s_full);
+        umma_commit(&k_empty[st]);  // K slot reusable once this QK^T has retired
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_qk(j + 1);
         const int st = j & 1;
+        TR_WAIT(tr_kv_full, mbar_wait(&v_full[st], (j >> 1) & 1));
         TR_WAIT(tr_p_full, mbar_wait_backoff(p_full, j & 1));  // P_j staged and (if it was needed) O rescaled
         tc_fence_after();
         const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes);
@@ -219,7 +237,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           umma_bf16_ss(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // accumulate across KV tiles in TMEM
         }
         umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
       }
       TR_PUT(5, tr_kv_full);
       TR_PUT(6, tr_s_empty);
@@ -328,7 +346,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 fma_f32x2(pack_f32x2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sl2_2, mneg_2);
             float x0, x1, p0, p1;
             unpack_f32x2(x, x0, x1);
-            if (pair_uses_poly(i >> 1)) {
+            if (pair_uses_poly<POLY>(i >> 1)) {
               exp2_poly_x2(x0, x1, p0, p1);
             } else {
               p0 = fast_exp2(x0);
@@ -410,28 +428,37 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-template <int DQ>
+template <int DQ, int POLY>
 static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream) {
   using Cfg = AttnCfg<DQ>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::kSmemBytes));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((p.lq + kTileQ - 1) / kTileQ, p.batch * p.heads, p.v_slices);
-  attention_kernel<DQ><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(q, k, v, p);
+  attention_kernel<DQ, POLY><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(q, k, v, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream) {
   switch (p.dqk_chunks) {
-    case 1: return launch_dq<1>(q, k, v, p, stream);
-    case 2: return launch_dq<2>(q, k, v, p, stream);
-    case 3: return launch_dq<3>(q, k, v, p, stream);
+    case 1: {
+      // CA_ATTN_POLY (developer knob): share of exponentials moved off the MUFU pipe, in eighths
+      static const int poly = getenv("CA_ATTN_POLY") ? atoi(getenv("CA_ATTN_POLY")) : kPolyDefault;
+      switch (poly) {
+        case 0: return launch_dq<1, 0>(q, k, v, p, stream);
+        case 3: return launch_dq<1, 3>(q, k, v, p, stream);
+        case 4: return launch_dq<1, 4>(q, k, v, p, stream);
+        default: return launch_dq<1, kPolyDefault>(q, k, v, p, stream);
+      }
+    }
+    case 2: return launch_dq<2, kPolyDefault>(q, k, v, p, stream);
+    case 3: return launch_dq<3, kPolyDefault>(q, k, v, p, stream);
     default: return cudaErrorInvalidValue;
   }
 }

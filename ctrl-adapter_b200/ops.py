@@ -416,10 +416,14 @@ def group_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     ct = c + c2
     nsamp = n // imgs_per_sample
     sums = torch.empty(nsamp * groups * 2, device=x.device, dtype=torch.float64)
+    if PROFILER.active:
+        NOTE[0] = f"gn_stats n{n} {h}x{w_} c{c}+{c2}"
     _launch("groupnorm", 0.0, 2.0 * n * h * w_ * ct, "ca_groupnorm_stats", x.data_ptr(), c, _ptr(x2), c2, nsamp,
             imgs_per_sample * h * w_, groups, sums.data_ptr(), _stream())
     if out is None:
         out = torch.empty((n, h * 2, w_ * 2, ct) if up2x else (n, h, w_, ct), device=x.device, dtype=BF16)
+    if PROFILER.active:
+        NOTE[0] = f"gn_apply n{n} {h}x{w_} c{c}+{c2} silu{int(silu)} up{int(up2x)}"
     _launch("groupnorm", 0.0, 2.0 * n * h * w_ * ct * (5 if up2x else 2), "ca_groupnorm_apply", x.data_ptr(), c,
             _ptr(x2), c2, n, h, w_, imgs_per_sample, groups, float(eps), sums.data_ptr(), gamma.data_ptr(),
             beta.data_ptr(), int(silu), int(up2x), out.data_ptr(), _stream())
@@ -433,6 +437,8 @@ def layer_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     rows = x.numel() // c
     y = torch.empty_like(x)
     ysum = torch.empty_like(x) if (add_rowvec is not None and return_sum) else None
+    if PROFILER.active:
+        NOTE[0] = f"layernorm rows{rows} c{c} rv{int(add_rowvec is not None)}"
     _launch("layernorm", 0.0, 2.0 * 2 * x.numel(), "ca_layernorm", x.data_ptr(), rows, c, float(eps), gamma.data_ptr(), beta.data_ptr(),
                                    _ptr(add_rowvec), rows_per_vec, _ptr(ysum), y.data_ptr(), _stream())
     return (y, ysum) if return_sum else y
