@@ -101,8 +101,11 @@ template <int R>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
 // blocked for a long time by design (producer on a free K/V slot, MMA issuer on the softmax): poll politely
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  int polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls > 8 && ns > 0) __nanosleep(ns);  // short waits never sleep
+  }
 }
 
 template <int DQ, int POLY>
@@ -128,22 +131,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* s_empty = bars + 6;
   uint64_t* p_full = bars + 7;
   uint64_t* o_full = bars + 8;
+  uint64_t* q_empty = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTileQ;
-  const int b = blockIdx.y / p.heads;
-  const int h = blockIdx.y % p.heads;
-  const int vs = blockIdx.z;
   const int dpad = 64 * p.v_slices;  // padded head dim (elements) in the Q/K/V channel layout
   const int nkv = (p.lk + kTileKV - 1) / kTileKV;
+  // persistent CTA: work item w = (v slice, batch*head, query tile), query tile fastest so that the CTAs running at the
+  // same time share K/V through L2.  Each role walks the same item sequence; barrier parities come from per-CTA counters
+  // (it = items done, g = KV tiles done) so the pipelines run straight across item boundaries: the next item's Q / K
+  // loads and first QK^T overlap this item's last softmax, PV and output write.
+  const int nqt = (p.lq + kTileQ - 1) / kTileQ;
+  const int total_items = nqt * p.batch * p.heads * p.v_slices;
+  auto decode = [&](int w, int& q0, int& b, int& h, int& vs) {
+    q0 = (w % nqt) * kTileQ;
+    const int bh = (w / nqt) % (p.batch * p.heads);
+    vs = w / (nqt * p.batch * p.heads);
+    b = bh / p.heads;
+    h = bh % p.heads;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -169,27 +183,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
   if (warp == 0) {
     if (lane == 0) {
-      const int kvb = b / p.kv_batch_div;
       TR_DECL(tr_kv_empty);
-      mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
-      for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
-      auto load_k = [&](int j) {
-        const int st = j & 1;
+      uint32_t it = 0, g = 0;  // items / KV tiles issued so far by this CTA
+      int q0, b, h, vs;
+      auto load_k = [&](int j, uint32_t gk, int kvb) {
+        const int st = gk & 1;
         uint8_t* dst = smem_kv + st * Cfg::kStageBytes;
-        TR_WAIT(tr_kv_empty, mbar_wait_backoff(&k_empty[st], ((j >> 1) & 1) ^ 1));
+        TR_WAIT(tr_kv_empty, mbar_wait_backoff(&k_empty[st], ((gk >> 1) & 1) ^ 1, p.backoff_ns));
         mbar_arrive_expect_tx(&k_full[st], DQ * kChunkBytes);
         for (int c = 0; c < DQ; ++c)
           tma_load_3d(dst + c * kChunkBytes, &tmap_k, &k_full[st], h * dpad + c * 64, j * kTileKV, kvb);
       };
-      load_k(0);
-      for (int j = 0; j < nkv; ++j) {
-        // K(j+1) first: its slot frees when QK^T(j-1) retires, which precedes PV(j-2) (the condition for V(j))
-        if (j + 1 < nkv) load_k(j + 1);
-        const int st = j & 1;
-        TR_WAIT(tr_kv_empty, mbar_wait_backoff(&v_empty[st], ((j >> 1) & 1) ^ 1));
-        mbar_arrive_expect_tx(&v_full[st], kChunkBytes);
-        tma_load_3d(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes, &tmap_v, &v_full[st], h * dpad + vs * 64,
-                    j * kTileKV, kvb);
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++it) {
+        decode(w, q0, b, h, vs);
+        const int kvb = b / p.kv_batch_div;
+        mbar_wait_backoff(q_empty, (it & 1) ^ 1, p.backoff_ns);  // every QK^T of the previous item has retired
+        mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+        for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
+        load_k(0, g, kvb);
+        for (int j = 0; j < nkv; ++j, ++g) {
+          // K(j+1) first: its slot frees when QK^T(j-1) retires, which precedes PV(j-2) (the condition for V(j))
+          if (j + 1 < nkv) load_k(j + 1, g + 1, kvb);
+          const int st = g & 1;
+          TR_WAIT(tr_kv_empty, mbar_wait_backoff(&v_empty[st], ((g >> 1) & 1) ^ 1, p.backoff_ns));
+          mbar_arrive_expect_tx(&v_full[st], kChunkBytes);
+          tma_load_3d(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes, &tmap_v, &v_full[st], h * dpad + vs * 64,
+                      j * kTileKV, kvb);
+        }
       }
       TR_PUT(9, tr_kv_empty);
     }
@@ -202,11 +222,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       TR_DECL(tr_kv_full);
       TR_DECL(tr_s_empty);
       TR_DECL(tr_p_full);
+      TR_DECL(tr_q_full);
       [[maybe_unused]] const long long tr_start = TR_NOW();
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        TR_WAIT(tr_kv_full, mbar_wait(&k_full[st], (j >> 1) & 1));
-        TR_WAIT(tr_s_empty, mbar_wait(s_empty, (j & 1) ^ 1));  // softmax has read S of tile j-1 into registers
+      const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                           static_cast<int>(gridDim.x);
+      const uint32_t total_tiles = static_cast<uint32_t>(my_items) * nkv;
+      // QK^T of global tile gq (tile jq of item itq); waits for that item's Q when jq == 0
+      auto issue_qk = [&](uint32_t gq, int jq, uint32_t itq) {
+        const int st = gq & 1;
+        if (jq == 0) TR_WAIT(tr_q_full, mbar_wait_backoff(q_full, itq & 1, p.backoff_ns));
+        TR_WAIT(tr_kv_full, mbar_wait(&k_full[st], (gq >> 1) & 1));
+        TR_WAIT(tr_s_empty, mbar_wait(s_empty, (gq & 1) ^ 1));  // softmax has read S of the previous tile
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem_kv + st * Cfg::kStageBytes);
 #pragma unroll
@@ -219,34 +245,44 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
         umma_commit(s_full);
-        umma_commit(&k_empty[st]);  // K slot reusable once this QK^T has retired
+        umma_commit(&k_empty[st]);               // K slot reusable once this QK^T has retired
+        if (jq == nkv - 1) umma_commit(q_empty);  // ... and so is Q after the item's last QK^T
       };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) issue_qk(j + 1);
-        const int st = j & 1;
-        TR_WAIT(tr_kv_full, mbar_wait(&v_full[st], (j >> 1) & 1));
-        TR_WAIT(tr_p_full, mbar_wait_backoff(p_full, j & 1));  // P_j staged and (if it was needed) O rescaled
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes);
+      if (total_tiles > 0) issue_qk(0, 0, 0);
+      uint32_t g = 0;
+      for (int it = 0; it < my_items; ++it) {
+        for (int j = 0; j < nkv; ++j, ++g) {
+          // look-ahead QK^T of the same item goes first; the first QK^T of the NEXT item waits for that item's Q, so it
+          // is issued after this item's last PV instead of delaying it (and with it the output write)
+          if (j + 1 < nkv) issue_qk(g + 1, j + 1, it);
+          const int st = g & 1;
+          TR_WAIT(tr_kv_full, mbar_wait(&v_full[st], (g >> 1) & 1));
+          TR_WAIT(tr_p_full, mbar_wait_backoff(p_full, g & 1, p.backoff_ns));  // P staged and (if it was needed) O rescaled
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * kChunkBytes + (k & 3) * 32, 16, 1024);
-          const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
-          umma_bf16_ss(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // accumulate across KV tiles in TMEM
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * kChunkBytes + (k & 3) * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
+            umma_bf16_ss(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // accumulate across KV tiles in TMEM
+          }
+          umma_commit(o_full);
+          umma_commit(&v_empty[st]);
+          if (j + 1 == nkv && g + 1 < total_tiles) issue_qk(g + 1, 0, it + 1);
         }
-        umma_commit(o_full);
-        umma_commit(&v_empty[st]);
       }
       TR_PUT(5, tr_kv_full);
       TR_PUT(6, tr_s_empty);
       TR_PUT(7, tr_p_full);
+      TR_PUT(10, tr_q_full);
       TR_PUT(8, TR_NOW() - tr_start);
     }
   } else if (warp >= 4) {
     // ===================== softmax / output: one thread per query row =====================
     if constexpr (DQ == 1) setmaxnreg_inc<232>();
+    // the two persistent CTAs of an SM start together; offset one of them by about half a KV tile so their MUFU-heavy
+    // exp phases interleave instead of colliding (whichever way the hardware pairs block ids onto SMs)
+    if (p.stagger_ns > 0 && gridDim.x > 148 && (((blockIdx.x / 148) ^ blockIdx.x) & 1)) __nanosleep(p.stagger_ns);
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
@@ -259,13 +295,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     TR_DECL(tr_o_full);
     TR_DECL(tr_ld);
     TR_DECL(tr_resc);
+    TR_DECL(tr_epi_o);
     [[maybe_unused]] const long long tr_start = TR_NOW();
 
-    auto tile_step = [&](auto mask_tag, int j, int kv_valid) {
+    auto tile_step = [&](auto mask_tag, int j, uint32_t g, int kv_valid) {
       constexpr bool MASK = decltype(mask_tag)::value;
-      TR_WAIT(tr_s_full, mbar_wait(s_full, j & 1));
+      TR_WAIT(tr_s_full, mbar_wait(s_full, g & 1));
       tc_fence_after();
       uint32_t sv[4][32];
+      // partial last KV tile: only the 32-column chunks that hold a valid key are processed (the P columns
+      // of the others are written as zeros); inside the boundary chunk invalid scores become -inf before the max, so the
+      // exp code below is the same as for a full tile
+      const int nch = MASK ? (kv_valid + 31) >> 5 : 4;
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_s + lane_sel + c * 32, sv[c]);
       TR_WAIT(tr_ld, tmem_ld_wait());
@@ -276,17 +317,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        if (MASK && c >= nch) continue;
+        if constexpr (MASK) {  // invalid scores of the boundary chunk become -inf, in place (exp2 -> 0)
+          const int lim = kv_valid - c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[c][i] = (i < lim) ? sv[c][i] : 0xff800000u;
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          float s0 = __uint_as_float(sv[c][i]), s1 = __uint_as_float(sv[c][i + 1]);
-          float s2 = __uint_as_float(sv[c][i + 2]), s3 = __uint_as_float(sv[c][i + 3]);
-          if (MASK) {
-            if (c * 32 + i >= kv_valid) s0 = -INFINITY;
-            if (c * 32 + i + 1 >= kv_valid) s1 = -INFINITY;
-            if (c * 32 + i + 2 >= kv_valid) s2 = -INFINITY;
-            if (c * 32 + i + 3 >= kv_valid) s3 = -INFINITY;
-          }
-          mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1); mx2 = fmaxf(mx2, s2); mx3 = fmaxf(mx3, s3);
+          mx0 = fmaxf(mx0, __uint_as_float(sv[c][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[c][i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[c][i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[c][i + 3]));
         }
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
@@ -300,7 +342,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #ifdef CA_TRACE
           ++tr_resc;
 #endif
-          mbar_wait(o_full, (j - 1) & 1);  // PV of tile j-1 has landed in O
+          mbar_wait(o_full, (g - 1) & 1);  // PV of tile j-1 has landed in O
           tc_fence_after();
           waited_o = true;
           const float alpha = need ? fast_exp2((m_used - m_tile) * sl2) : 1.0f;
@@ -320,26 +362,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       // ---- p = exp2(s*sl2 - m_used*sl2) (<= 2^8), row sum, bf16 P ----
       const float mneg = -m_used * sl2;
-      float rs0 = 0.f, rs1 = 0.f;
-      if constexpr (MASK) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), sl2, mneg));
-            float p1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), sl2, mneg));
-            if (c * 32 + i >= kv_valid) p0 = 0.f;
-            if (c * 32 + i + 1 >= kv_valid) p1 = 0.f;
-            rs0 += p0;
-            rs1 += p1;
-            sv[c][i >> 1] = pack_bf16x2(p0, p1);  // packed P overwrites the already consumed scores in place
-          }
-        }
-      } else {
+      float rs0, rs1;
+      {
         const uint64_t sl2_2 = pack_f32x2(sl2, sl2), mneg_2 = pack_f32x2(mneg, mneg);
         uint64_t rs_a = pack_f32x2(0.f, 0.f), rs_b = rs_a;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+          if (MASK && c >= nch) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sv[c][i] = 0u;  // P = 0 for keys that do not exist
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint64_t x =
@@ -347,25 +380,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             float x0, x1, p0, p1;
             unpack_f32x2(x, x0, x1);
             if (pair_uses_poly<POLY>(i >> 1)) {
-              exp2_poly_x2(x0, x1, p0, p1);
+              exp2_poly_x2(x0, x1, p0, p1);  // -inf (masked) is clamped: 2^-100, invisible next to a row sum >= 1
             } else {
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
             }
             if ((i >> 1) & 1) rs_b = add_f32x2(rs_b, pack_f32x2(p0, p1));
             else rs_a = add_f32x2(rs_a, pack_f32x2(p0, p1));
-            sv[c][i >> 1] = pack_bf16x2(p0, p1);
+            sv[c][i >> 1] = pack_bf16x2(p0, p1);  // packed P overwrites the already consumed scores in place
           }
         }
-        float a0, a1;
-        unpack_f32x2(add_f32x2(rs_a, rs_b), a0, a1);
-        rs0 = a0;
-        rs1 = a1;
+        unpack_f32x2(add_f32x2(rs_a, rs_b), rs0, rs1);
       }
       l_run += rs0 + rs1;
       // P smem of tile j-1 must have been consumed by its PV MMA before it is overwritten
       if (j > 0 && !waited_o) {
-        TR_WAIT(tr_o_full, mbar_wait(o_full, (j - 1) & 1));
+        TR_WAIT(tr_o_full, mbar_wait(o_full, (g - 1) & 1));
         tc_fence_after();
       }
 #pragma unroll
@@ -383,10 +413,41 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     };
-    for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(kTileKV, p.lk - j * kTileKV);
-      if (kv_valid == kTileKV) tile_step(std::false_type{}, j, kv_valid);
-      else tile_step(std::true_type{}, j, kv_valid);
+    uint32_t g = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+      int q0, b, h, vs;
+      decode(w, q0, b, h, vs);
+      m_used = -INFINITY;
+      l_run = 0.f;
+      for (int j = 0; j < nkv; ++j, ++g) {
+        const int kv_valid = min(kTileKV, p.lk - j * kTileKV);
+        if (kv_valid == kTileKV) tile_step(std::false_type{}, j, g, kv_valid);
+        else tile_step(std::true_type{}, j, g, kv_valid);
+      }
+      // epilogue: O / l (the next item's first QK^T and its loads are already in flight)
+      TR_WAIT(tr_epi_o, mbar_wait(o_full, (g - 1) & 1));
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const int row = q0 + r;
+      __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_batch_stride +
+                            static_cast<long long>(row) * p.out_row_stride + h * dpad + vs * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
+        tmem_ld_wait();
+        if (row < p.lq) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(ov[u * 8 + e]) * inv_l;
+            *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = make_uint4(
+                pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
+        }
+      }
+      tc_fence_before();  // O reads ordered before the p_full arrive that lets the next item's first PV overwrite O
     }
     if (warp == 4 && lane == 0) {
       TR_PUT(0, TR_NOW() - tr_start);
@@ -394,31 +455,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       TR_PUT(2, tr_o_full);
       TR_PUT(3, tr_resc);
       TR_PUT(4, tr_ld);
+      TR_PUT(11, tr_epi_o);
     }
-    // epilogue: O / l
-    mbar_wait(o_full, (nkv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const int row = q0 + r;
-    __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_batch_stride +
-                          static_cast<long long>(row) * p.out_row_stride + h * dpad + vs * 64;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t ov[32];
-      tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
-      tmem_ld_wait();
-      if (row < p.lq) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(ov[u * 8 + e]) * inv_l;
-          *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = make_uint4(
-              pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-        }
-      }
-    }
-    tc_fence_before();
   }
 
   __syncthreads();
@@ -437,9 +475,24 @@ static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const C
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::kSmemBytes));
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attention_kernel<DQ, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((p.lq + kTileQ - 1) / kTileQ, p.batch * p.heads, p.v_slices);
+  static int resident = 0;  // CTAs the device holds at once: two per SM for head dim 64 (smem), else one
+  if (resident == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || sms < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
+    resident = sms * (DQ == 1 ? 2 : 1);
+  }
+  const long long items = static_cast<long long>((p.lq + kTileQ - 1) / kTileQ) * p.batch * p.heads * p.v_slices;
+  if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
+  // developer knobs: CA_ATTN_GRID=items launches one CTA per work item (hardware block scheduler, dynamic balance)
+  static const bool per_item = getenv("CA_ATTN_GRID") && getenv("CA_ATTN_GRID")[0] == 'i';
+  const int grid = static_cast<int>((items < resident || per_item) ? items : resident);
   attention_kernel<DQ, POLY><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(q, k, v, p);
   return cudaGetLastError();
 }

@@ -240,6 +240,10 @@ int ca_attention(const ca_attention_desc* d, void* cuda_stream) {
   p.batch = d->batch; p.heads = d->heads; p.lq = d->lq; p.lk = d->lk;
   p.kv_batch_div = kv_div;
   p.trace = trace_ptr();
+  static const unsigned stagger = getenv("CA_ATTN_STAGGER") ? static_cast<unsigned>(atoi(getenv("CA_ATTN_STAGGER"))) : 0u;
+  p.stagger_ns = stagger;
+  static const unsigned backoff = getenv("CA_ATTN_BACKOFF") ? static_cast<unsigned>(atoi(getenv("CA_ATTN_BACKOFF"))) : 64u;
+  p.backoff_ns = backoff;
   p.dqk_chunks = d->head_dim_pad / 64;
   p.v_slices = d->head_dim_pad / 64;
   p.scale_log2 = d->scale * 1.4426950408889634f;

@@ -49,6 +49,8 @@ struct AttnParams {
   __nv_bfloat16* out;  // [batch, lq, heads * 64 * v_slices]
   long long out_batch_stride, out_row_stride;  // elements
   unsigned long long* trace;  // -DCA_TRACE builds only
+  unsigned backoff_ns;        // nanosleep per poll of the producer / MMA warps once a wait has lasted a few polls
+  unsigned stagger_ns;        // start offset between the two persistent CTAs of an SM (0 = none)
 };
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream);

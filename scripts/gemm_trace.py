@@ -67,22 +67,28 @@ def main():
         "geglu 65536x640->5120": (lin(65536, 640, 5120, act=ops.ACT_GEGLU), 2.0 * 65536 * 640 * 5120),
         "conv3 16x128x128 320->320": (conv(16, 128, 320, 320), 2.0 * 16 * 128 * 128 * 2880 * 320),
     }
-    def attn(b, h, l):
+    def attn(b, h, l, lk=None):
         qkv = rnd(b, l, 3 * h * 64)
         q, k, v = qkv[:, :, : h * 64], qkv[:, :, h * 64: 2 * h * 64], qkv[:, :, 2 * h * 64:]
+        if lk is not None:
+            kv = rnd(b, lk, 2 * h * 64)
+            k, v = kv[:, :, : h * 64], kv[:, :, h * 64:]
         return lambda: ops.attention(q, k, v, h, 64, 0.125)
 
     attn_cases = {
         "attn b16 h5 16384": (attn(16, 5, 16384), 4.0 * 16 * 5 * 16384 * 16384 * 64),
         "attn b16 h10 4096": (attn(16, 10, 4096), 4.0 * 16 * 10 * 4096 * 4096 * 64),
         "attn b16 h20 1024": (attn(16, 20, 1024), 4.0 * 16 * 20 * 1024 * 1024 * 64),
+        "attn b16 h20 1024x77": (attn(16, 20, 1024, 77), 4.0 * 16 * 20 * 1024 * 77 * 64),
     }
     attn_names = ["sm_total", "sm_wait_s_full", "sm_wait_o_full", "sm_rescales", "sm_tmem_ld_wait", "mma_wait_kv_full",
-                  "mma_wait_s_empty", "mma_wait_p_full", "mma_total", "prod_wait_kv_empty"]
+                  "mma_wait_s_empty", "mma_wait_p_full", "mma_total", "prod_wait_kv_empty", "mma_wait_q_full",
+                  "sm_wait_o_full_epilogue"]
     gemm_names = ["prod_total", "prod_wait_empty", "mma_wait_full", "mma_wait_acc", "e0_wait_accfull", "e0_total", "e0_wait_cp",
              "e0_arrive", "mma_total", "e0_tiles", "e7_wait_accfull", "e7_total", "e7_wait_cp", "e7_arrive", "e7_tiles",
              "e0_tmem_wait"]
-    for name, (fn, flops) in list(cases.items()) + list(attn_cases.items()):
+    only_attn = "--attn" in sys.argv
+    for name, (fn, flops) in ([] if only_attn else list(cases.items())) + list(attn_cases.items()):
         names = attn_names if name in attn_cases else gemm_names
         for _ in range(3):
             fn()

@@ -43,11 +43,12 @@ elif which == "lin_res":
     res = rnd(16384, 1280)
     fn = lambda: ops.linear(x, w, bias, residual=res)  # noqa: E731
     flops = 2.0 * 16384 * 1280 * 1280
-elif which == "conv":
+elif which.startswith("conv"):  # conv or conv:<bn>
+    bn = int(which.split(":")[1]) if ":" in which else 0
     x = rnd(16, 128, 128, 320)
     w = ops.pack_conv_weight(rnd(320, 320, 3, 3, scale=1 / math.sqrt(2880)))
     bias = torch.zeros(320, device=dev)
-    fn = lambda: ops.conv2d(x, w, bias)  # noqa: E731
+    fn = lambda: ops.conv2d(x, w, bias, bn=bn)  # noqa: E731
     flops = 2.0 * 16 * 128 * 128 * 2880 * 320
 else:
     raise SystemExit(which)
