@@ -16,7 +16,8 @@
 //   * MUFU.EX2 (16 / clk / SM) is the scarcest pipe: a compile-time share of the exponentials (kPolyOf8 pairs out of
 //     8) is evaluated on the FMA pipe instead -- Cody-Waite split, cubic minimax 2^f on [-0.5, 0.5] (7.5e-5 relative,
 //     1/26 of a bf16 half-ulp of P), exponent spliced in with an integer add;
-//   * setmaxnreg moves registers from warpgroup 0 (24 each) to the softmax warpgroup (232 each) so the 128 scores of
+//   * setmaxnreg moves registers from warpgroup 0 to the softmax warpgroup (208 each; warpgroup 0 keeps 48 -- with
+//     fewer the MMA issuer spills its descriptors and every tcgen05.mma issue costs hundreds of cycles) so the 128 scores of
 //     a row stay in registers without spills while two CTAs still share an SM;
 //   * the producer / MMA warps back off with nanosleep while blocked so their polling does not steal issue slots.
 // With head dim 64 the CTA uses 113 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's softmax overlaps
@@ -108,7 +109,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
-template <int DQ, int POLY>
+template <int DQ, int POLY, bool PT>
 __global__ void __launch_bounds__(kAttnThreads, (DQ == 1) ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -177,14 +178,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
+  [[maybe_unused]] const uint32_t tmem_p = tmem_base + 192;  // PT: bf16 P, two keys per 32-bit cell, 64 columns
 
   if (warp < 4) {
-    if constexpr (DQ == 1) setmaxnreg_dec<24>();
+    if constexpr (DQ == 1) setmaxnreg_dec<48>();
   }
   if (warp == 0) {
     if (lane == 0) {
       TR_DECL(tr_kv_empty);
       uint32_t it = 0, g = 0;  // items / KV tiles issued so far by this CTA
+      TR_EVT_DECL(0);
       int q0, b, h, vs;
       auto load_k = [&](int j, uint32_t gk, int kvb) {
         const int st = gk & 1;
@@ -198,9 +201,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         decode(w, q0, b, h, vs);
         const int kvb = b / p.kv_batch_div;
         mbar_wait_backoff(q_empty, (it & 1) ^ 1, p.backoff_ns);  // every QK^T of the previous item has retired
+        TR_EVT(1);
         mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
         for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
         load_k(0, g, kvb);
+        TR_EVT(2);
         for (int j = 0; j < nkv; ++j, ++g) {
           // K(j+1) first: its slot frees when QK^T(j-1) retires, which precedes PV(j-2) (the condition for V(j))
           if (j + 1 < nkv) load_k(j + 1, g + 1, kvb);
@@ -209,6 +214,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           mbar_arrive_expect_tx(&v_full[st], kChunkBytes);
           tma_load_3d(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes, &tmap_v, &v_full[st], h * dpad + vs * 64,
                       j * kTileKV, kvb);
+          TR_EVT(3);
         }
       }
       TR_PUT(9, tr_kv_empty);
@@ -218,11 +224,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V tile) is MN-major
       const uint32_t q_addr = smem_u32(smem_q);
-      const uint32_t p_addr = smem_u32(smem_p);
+      [[maybe_unused]] const uint32_t p_addr = smem_u32(smem_p);
       TR_DECL(tr_kv_full);
       TR_DECL(tr_s_empty);
       TR_DECL(tr_p_full);
       TR_DECL(tr_q_full);
+      TR_EVT_DECL(96);
       [[maybe_unused]] const long long tr_start = TR_NOW();
       const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                            static_cast<int>(gridDim.x);
@@ -231,8 +238,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       auto issue_qk = [&](uint32_t gq, int jq, uint32_t itq) {
         const int st = gq & 1;
         if (jq == 0) TR_WAIT(tr_q_full, mbar_wait_backoff(q_full, itq & 1, p.backoff_ns));
+        TR_EVT(10);
         TR_WAIT(tr_kv_full, mbar_wait(&k_full[st], (gq >> 1) & 1));
         TR_WAIT(tr_s_empty, mbar_wait(s_empty, (gq & 1) ^ 1));  // softmax has read S of the previous tile
+        TR_EVT(11);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(smem_kv + st * Cfg::kStageBytes);
 #pragma unroll
@@ -247,6 +256,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         umma_commit(s_full);
         umma_commit(&k_empty[st]);               // K slot reusable once this QK^T has retired
         if (jq == nkv - 1) umma_commit(q_empty);  // ... and so is Q after the item's last QK^T
+        TR_EVT(12);
       };
       if (total_tiles > 0) issue_qk(0, 0, 0);
       uint32_t g = 0;
@@ -257,17 +267,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (j + 1 < nkv) issue_qk(g + 1, j + 1, it);
           const int st = g & 1;
           TR_WAIT(tr_kv_full, mbar_wait(&v_full[st], (g >> 1) & 1));
+          TR_EVT(13);
           TR_WAIT(tr_p_full, mbar_wait_backoff(p_full, g & 1, p.backoff_ns));  // P staged and (if it was needed) O rescaled
+          TR_EVT(14);
           tc_fence_after();
           const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + DQ * kChunkBytes);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * kChunkBytes + (k & 3) * 32, 16, 1024);
             const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
-            umma_bf16_ss(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // accumulate across KV tiles in TMEM
+            if constexpr (PT) {
+              umma_bf16_ts(tmem_o, tmem_p + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // 16 keys = 8 TMEM cells
+            } else {
+              const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * kChunkBytes + (k & 3) * 32, 16, 1024);
+              umma_bf16_ss(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // accumulate across KV tiles in TMEM
+            }
           }
           umma_commit(o_full);
           umma_commit(&v_empty[st]);
+          TR_EVT(15);
           if (j + 1 == nkv && g + 1 < total_tiles) issue_qk(g + 1, 0, it + 1);
         }
       }
@@ -279,7 +296,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== softmax / output: one thread per query row =====================
-    if constexpr (DQ == 1) setmaxnreg_inc<232>();
+    if constexpr (DQ == 1) setmaxnreg_inc<208>();
     // the two persistent CTAs of an SM start together; offset one of them by about half a KV tile so their MUFU-heavy
     // exp phases interleave instead of colliding (whichever way the hardware pairs block ids onto SMs)
     if (p.stagger_ns > 0 && gridDim.x > 148 && (((blockIdx.x / 148) ^ blockIdx.x) & 1)) __nanosleep(p.stagger_ns);
@@ -289,18 +306,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const float sl2 = p.scale_log2;
     float m_used = -INFINITY;  // the max (raw score units) the accumulated P / O / l are expressed against
     float l_run = 0.f;
-    uint8_t* p_row = smem_p + r * 128;
-    const int sw = r & 7;
+    [[maybe_unused]] uint8_t* p_row = smem_p + r * 128;
+    [[maybe_unused]] const int sw = r & 7;
     TR_DECL(tr_s_full);
     TR_DECL(tr_o_full);
     TR_DECL(tr_ld);
     TR_DECL(tr_resc);
     TR_DECL(tr_epi_o);
+    TR_EVT_DECL(192);
+    [[maybe_unused]] const bool tr_me = (warp == 4 && lane == 0);
     [[maybe_unused]] const long long tr_start = TR_NOW();
 
     auto tile_step = [&](auto mask_tag, int j, uint32_t g, int kv_valid) {
       constexpr bool MASK = decltype(mask_tag)::value;
       TR_WAIT(tr_s_full, mbar_wait(s_full, g & 1));
+      if (tr_me) TR_EVT(20);
       tc_fence_after();
       uint32_t sv[4][32];
       // partial last KV tile: only the 32-column chunks that hold a valid key are processed (the P columns
@@ -313,6 +333,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite the TMEM buffer
+      if (tr_me) TR_EVT(21);
       // ---- row max ----
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -393,25 +414,42 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         unpack_f32x2(add_f32x2(rs_a, rs_b), rs0, rs1);
       }
       l_run += rs0 + rs1;
-      // P smem of tile j-1 must have been consumed by its PV MMA before it is overwritten
+      if (tr_me) TR_EVT(22);
+      // P of tile j-1 must have been consumed by its PV MMA before it is overwritten
       if (j > 0 && !waited_o) {
         TR_WAIT(tr_o_full, mbar_wait(o_full, (g - 1) & 1));
         tc_fence_after();
       }
+      if constexpr (PT) {
+        // P goes to tensor memory (the PV MMA reads its A operand from there): no shared-memory stores, no proxy fence
+        uint32_t pw[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint8_t* chunk = p_row + (c >> 1) * kChunkBytes;
+        for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 128-byte row
-          *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) =
-              make_uint4(sv[c][u * 4], sv[c][u * 4 + 1], sv[c][u * 4 + 2], sv[c][u * 4 + 3]);
+          for (int i = 0; i < 16; ++i) {
+            pw[i] = sv[2 * hh][i];
+            pw[16 + i] = sv[2 * hh + 1][i];
+          }
+          tmem_st_32x32(tmem_p + lane_sel + hh * 32, pw);
         }
+        tmem_st_wait();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint8_t* chunk = p_row + (c >> 1) * kChunkBytes;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 128-byte row
+            *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) =
+                make_uint4(sv[c][u * 4], sv[c][u * 4 + 1], sv[c][u * 4 + 2], sv[c][u * 4 + 3]);
+          }
+        }
+        fence_proxy_async_smem();  // P stores -> visible to the tensor core (async proxy)
       }
-      fence_proxy_async_smem();  // P stores -> visible to the tensor core (async proxy)
       tc_fence_before();         // orders the tcgen05.st of a rescale before the MMA that follows the barrier
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      if (tr_me) TR_EVT(23);
     };
     uint32_t g = 0;
     for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
@@ -426,6 +464,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       // epilogue: O / l (the next item's first QK^T and its loads are already in flight)
       TR_WAIT(tr_epi_o, mbar_wait(o_full, (g - 1) & 1));
+      if (tr_me) TR_EVT(24);
       tc_fence_after();
       const float inv_l = 1.0f / l_run;
       const int row = q0 + r;
@@ -447,6 +486,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
       }
+      if (tr_me) TR_EVT(25);
       tc_fence_before();  // O reads ordered before the p_full arrive that lets the next item's first PV overwrite O
     }
     if (warp == 4 && lane == 0) {
@@ -466,16 +506,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-template <int DQ, int POLY>
+template <int DQ, int POLY, bool PT>
 static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream) {
   using Cfg = AttnCfg<DQ>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::kSmemBytes));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attention_kernel<DQ, POLY>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, PT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -493,7 +533,7 @@ static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const C
   // developer knobs: CA_ATTN_GRID=items launches one CTA per work item (hardware block scheduler, dynamic balance)
   static const bool per_item = getenv("CA_ATTN_GRID") && getenv("CA_ATTN_GRID")[0] == 'i';
   const int grid = static_cast<int>((items < resident || per_item) ? items : resident);
-  attention_kernel<DQ, POLY><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(q, k, v, p);
+  attention_kernel<DQ, POLY, PT><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(q, k, v, p);
   return cudaGetLastError();
 }
 
@@ -501,17 +541,19 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
                              cudaStream_t stream) {
   switch (p.dqk_chunks) {
     case 1: {
-      // CA_ATTN_POLY (developer knob): share of exponentials moved off the MUFU pipe, in eighths
+      // developer knobs: CA_ATTN_POLY = share of exponentials moved off the MUFU pipe (eighths);
+      // CA_ATTN_PSMEM=1 stages P through shared memory (SS MMA) instead of tensor memory (TS MMA)
       static const int poly = getenv("CA_ATTN_POLY") ? atoi(getenv("CA_ATTN_POLY")) : kPolyDefault;
+      static const bool psmem = getenv("CA_ATTN_PSMEM") != nullptr;
+      if (psmem) return launch_dq<1, kPolyDefault, false>(q, k, v, p, stream);
       switch (poly) {
-        case 0: return launch_dq<1, 0>(q, k, v, p, stream);
-        case 3: return launch_dq<1, 3>(q, k, v, p, stream);
-        case 4: return launch_dq<1, 4>(q, k, v, p, stream);
-        default: return launch_dq<1, kPolyDefault>(q, k, v, p, stream);
+        case 0: return launch_dq<1, 0, true>(q, k, v, p, stream);
+        case 3: return launch_dq<1, 3, true>(q, k, v, p, stream);
+        default: return launch_dq<1, kPolyDefault, true>(q, k, v, p, stream);
       }
     }
-    case 2: return launch_dq<2, kPolyDefault>(q, k, v, p, stream);
-    case 3: return launch_dq<3, kPolyDefault>(q, k, v, p, stream);
+    case 2: return launch_dq<2, kPolyDefault, true>(q, k, v, p, stream);
+    case 3: return launch_dq<3, kPolyDefault, true>(q, k, v, p, stream);
     default: return cudaErrorInvalidValue;
   }
 }

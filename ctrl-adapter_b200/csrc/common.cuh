@@ -160,6 +160,17 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (K-major, 16-bit elements packed two per 32-bit TMEM cell, one row per
+// lane) is read straight from tensor memory -- used for P in softmax(QK^T) V so P never touches shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 32 columns of fp32: thread i of the warp receives lane (base_lane + i), columns [col, col+32)
@@ -313,9 +324,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
 #define TR_WAIT(v_, stmt) do { const long long _t0 = clock64(); stmt; v_ += clock64() - _t0; } while (0)
 #define TR_PUT(slot, v_) do { if (p.trace != nullptr && TR_CTA() < 4096) p.trace[TR_CTA() * 16 + (slot)] = static_cast<unsigned long long>(v_); } while (0)
 #define TR_NOW() clock64()
+// event log of CTA 0 (behind the per-CTA counters): (event id, clock) pairs, first 96 events of each logging thread
+#define TR_EVT_DECL(base_) int _evt_n = 0; const int _evt_base = (base_)
+#define TR_EVT(id_) do { if (p.trace != nullptr && TR_CTA() == 0 && _evt_n < 96) { p.trace[16 * 4096 + (_evt_base + _evt_n) * 2] = (id_); p.trace[16 * 4096 + (_evt_base + _evt_n) * 2 + 1] = static_cast<unsigned long long>(clock64()); ++_evt_n; } } while (0)
 #else
 #define TR_DECL(v_)
 #define TR_WAIT(v_, stmt) stmt
 #define TR_PUT(slot, v_)
 #define TR_NOW() 0
+#define TR_EVT_DECL(base_)
+#define TR_EVT(id_)
 #endif

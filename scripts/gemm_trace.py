@@ -31,7 +31,7 @@ def build():
 
 def main():
     import torch
-    n_slots = 16 * 4096
+    n_slots = 16 * 4096 + 2 * 288
     trace = torch.zeros(n_slots, dtype=torch.int64, device="cuda")
     os.environ["CA_B200_LIB"] = TRACE_LIB
     os.environ["CA_GEMM_TRACE_PTR"] = hex(trace.data_ptr())
@@ -90,6 +90,8 @@ def main():
     only_attn = "--attn" in sys.argv
     for name, (fn, flops) in ([] if only_attn else list(cases.items())) + list(attn_cases.items()):
         names = attn_names if name in attn_cases else gemm_names
+        if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] not in name:
+            continue
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -103,7 +105,13 @@ def main():
         trace.zero_()
         fn()
         torch.cuda.synchronize()
-        t = trace.view(-1, 16).cpu().double()
+        if "--events" in sys.argv and name in attn_cases:
+            ev = trace[16 * 4096:].view(-1, 2).cpu().tolist()
+            rows = sorted([(c, int(i), src) for src, lo in (("prod", 0), ("mma", 96), ("smx", 192))
+                           for i, c in ev[lo:lo + 96] if c > 0])
+            t0 = rows[0][0] if rows else 0
+            print("   events (clk since first, src, id): " + " ".join(f"{c - t0}:{src}{i}" for c, i, src in rows[:120]))
+        t = trace[:16 * 4096].view(-1, 16).cpu().double()
         used = t[t[:, 0] > 0][:2048]
         lead = used[used[:, 8] > 0]
         print(f"== {name}: {ms * 1e3:.1f} us  {flops / ms / 1e9:.0f} TFLOP/s  ctas={used.shape[0]}")
