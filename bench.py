@@ -217,12 +217,31 @@ def run_reference_arm(a):
                                    "one pipeline-loop iteration per step", "sample": info["sample"]},
             "cpu_baseline": info,
             "e2e": {"value": rate, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout: route everything libraries print there (e.g. NCCL's version banner)
+    to stderr and keep the real stdout for emit()."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     a = parse()
+    _quiet_stdout()
     if a.impl == "reference":
         run_reference_arm(a)
         return
@@ -479,7 +498,7 @@ def main():
             "launches_per_step": launches_per_step, "roofline": roofline, "kernel_families": families,
             "cpu_baseline": cpu_baseline, "eager_gpu_baseline": eager_gpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.destroy_process_group()
 
