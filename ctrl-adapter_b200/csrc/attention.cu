@@ -56,25 +56,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// ---- packed fp32x2 arithmetic (FFMA2 / FADD2: two lanes per issued instruction) ----
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // 2^x for a pair on the FMA / ALU pipes only.  x <= 8 by construction; clamped below so the exponent splice cannot wrap
 // (anything under 2^-100 is irrelevant next to a row sum >= 2^-8).
 __device__ __forceinline__ void exp2_poly_x2(float x0, float x1, float& p0, float& p1) {

@@ -110,21 +110,23 @@ cudaError_t launch_gn_stats(const __nv_bfloat16* x0, int c0, const __nv_bfloat16
 // ---------------------------------------------------------------------------------------------
 // GroupNorm apply (+SiLU, +2x nearest upsample, +concat of two sources), bf16 out.
 // grid (pixel slabs, images); image i uses the statistics of sample i / imgs_per_sample.
-// Per-channel scale/shift (gamma*rstd, beta - mean*gamma*rstd) are staged in shared memory once per block.
+// Same thread mapping as the statistics pass: a thread owns ONE 8-channel vector column for the whole slab, so its 8
+// scale / shift pairs (gamma*rstd, beta - mean*gamma*rstd) live in registers and the pixel loop is pure streaming --
+// 4 independent 16-byte loads in flight, no index arithmetic beyond one add per pixel, no shared-memory reads.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <bool SILU, bool UP>
+__global__ void __launch_bounds__(512)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1, int h,
                 int w, int imgs_per_sample, int groups, float eps, const double* __restrict__ sums,
-                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, int up2x, int pix_per_block,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int pix_per_block,
                 __nv_bfloat16* __restrict__ y) {
-  extern __shared__ float s_ab[];  // [C] scale, [C] shift
   __shared__ float s_mean[64], s_rstd[64];
   const int C = c0 + c1;
   const int nvec = C >> 3;
   const int cpg = C / groups;
   const int img = blockIdx.y;
   const int sample = img / imgs_per_sample;
-  const long long hw = static_cast<long long>(h) * w;
+  const int hw = h * w;
   if (threadIdx.x < groups) {
     const double cnt = static_cast<double>(hw) * imgs_per_sample * cpg;
     const double s = sums[(static_cast<long long>(sample) * groups + threadIdx.x) * 2];
@@ -136,58 +138,59 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
     s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float a = s_rstd[g] * __ldg(gamma + c);
-    s_ab[c] = a;
-    s_ab[C + c] = __ldg(beta + c) - s_mean[g] * a;
+  const int rows_per_iter = blockDim.x / nvec;  // the launcher makes blockDim.x an exact multiple of nvec
+  const int vec = threadIdx.x % nvec;
+  const int rsub = threadIdx.x / nvec;
+  const int ch = vec * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int g = (ch + e) / cpg;
+    sc[e] = s_rstd[g] * __ldg(gamma + ch + e);
+    sh[e] = __ldg(beta + ch + e) - s_mean[g] * sc[e];
   }
-  __syncthreads();
-  const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_block;
-  const long long p_end = min(hw, p_begin + pix_per_block);
-  const long long total = (p_end - p_begin) * nvec;
-  const __nv_bfloat16* img0 = x0 + static_cast<long long>(img) * hw * c0;
-  const __nv_bfloat16* img1 = x1 ? x1 + static_cast<long long>(img) * hw * c1 : nullptr;
-  for (long long idx0 = threadIdx.x; idx0 < total; idx0 += 2LL * blockDim.x) {
-    uint4 u[2];
-    long long pix[2];
-    int ch[2];
-    bool ok[2];
+  const bool second = ch >= c0;
+  const int cs = second ? c1 : c0;
+  const __nv_bfloat16* src = (second ? x1 + (ch - c0) : x0 + ch) + static_cast<long long>(img) * hw * cs;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(hw, p_begin + pix_per_block);
+
+  auto emit = [&](const uint4& u, int pix) {
+    const uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const long long idx = idx0 + static_cast<long long>(k) * blockDim.x;
-      ok[k] = idx < total;
-      pix[k] = p_begin + (ok[k] ? idx / nvec : 0);
-      ch[k] = static_cast<int>((ok[k] ? idx % nvec : 0)) * 8;
-      const __nv_bfloat16* src = (ch[k] >= c0) ? img1 + pix[k] * c1 + (ch[k] - c0) : img0 + pix[k] * c0 + ch[k];
-      if (ok[k]) u[k] = ld_nc(src);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (!ok[k]) continue;
-      const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&u[k]);
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float v = fmaf(__bfloat162float(hv[e]), s_ab[ch[k] + e], s_ab[C + ch[k] + e]);
-        if (silu) v = v / (1.0f + __expf(-v));
-        f[e] = v;
+    for (int e = 0; e < 4; ++e) {
+      float v0 = fmaf(bf16lo_to_float(wds[e]), sc[2 * e], sh[2 * e]);
+      float v1 = fmaf(bf16hi_to_float(wds[e]), sc[2 * e + 1], sh[2 * e + 1]);
+      if (SILU) {
+        v0 = __fdividef(v0, 1.0f + __expf(-v0));
+        v1 = __fdividef(v1, 1.0f + __expf(-v1));
       }
-      const uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                 pack_bf16x2(f[6], f[7]));
-      if (!up2x) {
-        *reinterpret_cast<uint4*>(y + (static_cast<long long>(img) * hw + pix[k]) * C + ch[k]) = o;
-      } else {
-        const int py = static_cast<int>(pix[k] / w), px = static_cast<int>(pix[k] % w);
-        const long long ow = 2LL * w;
-        __nv_bfloat16* dst = y + ((static_cast<long long>(img) * 2 * h + 2 * py) * ow + 2 * px) * C + ch[k];
-        *reinterpret_cast<uint4*>(dst) = o;
-        *reinterpret_cast<uint4*>(dst + C) = o;
-        *reinterpret_cast<uint4*>(dst + ow * C) = o;
-        *reinterpret_cast<uint4*>(dst + ow * C + C) = o;
-      }
+      o[e] = pack_bf16x2(v0, v1);
     }
+    const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+    if (!UP) {
+      *reinterpret_cast<uint4*>(y + (static_cast<long long>(img) * hw + pix) * C + ch) = ov;
+    } else {
+      const int py = pix / w, px = pix - py * w;
+      const long long ow = 2LL * w;
+      __nv_bfloat16* dst = y + ((static_cast<long long>(img) * 2 * h + 2 * py) * ow + 2 * px) * C + ch;
+      *reinterpret_cast<uint4*>(dst) = ov;
+      *reinterpret_cast<uint4*>(dst + C) = ov;
+      *reinterpret_cast<uint4*>(dst + ow * C) = ov;
+      *reinterpret_cast<uint4*>(dst + ow * C + C) = ov;
+    }
+  };
+
+  int pix = p_begin + rsub;
+  for (; pix + 3 * rows_per_iter < p_end; pix += 4 * rows_per_iter) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = ld_nc(src + static_cast<long long>(pix + k * rows_per_iter) * cs);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(u[k], pix + k * rows_per_iter);
   }
+  for (; pix < p_end; pix += rows_per_iter) emit(ld_nc(src + static_cast<long long>(pix) * cs), pix);
 }
 
 cudaError_t launch_gn_apply(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, int c1, int n, int h, int w,
@@ -196,23 +199,38 @@ cudaError_t launch_gn_apply(const __nv_bfloat16* x0, int c0, const __nv_bfloat16
   const int C = c0 + c1;
   if (groups > 64 || C % groups != 0 || (C & 7) != 0 || (c0 & 7) != 0 || C > 4096) return cudaErrorInvalidValue;
   const long long hw = static_cast<long long>(h) * w;
-  long long want_blocks = (148LL * 8 + n - 1) / n;
-  long long ppb = (hw + want_blocks - 1) / want_blocks;
-  if (ppb < 16) ppb = 16;
+  if (hw > 0x3fffffffLL) return cudaErrorInvalidValue;
+  const int nvec = C >> 3;
+  const int rows_per_iter = 512 / nvec;  // >= 1 because C <= 4096
+  const int threads = rows_per_iter * nvec;
+  // about 6 slabs per SM over the whole launch, each a multiple of the 4-row unrolled step
+  long long want_blocks = (148LL * 6 + n - 1) / n;
+  const long long step = 4LL * rows_per_iter;
+  long long ppb = ((hw + want_blocks - 1) / want_blocks + step - 1) / step * step;
+  if (ppb < 2 * step) ppb = 2 * step;
   const int slabs = static_cast<int>((hw + ppb - 1) / ppb);
-  gn_apply_kernel<<<dim3(slabs, n), 256, 2 * C * sizeof(float), stream>>>(x0, c0, x1, c1, h, w, imgs_per_sample, groups,
-                                                                          eps, sums, gamma, beta, silu, up2x,
-                                                                          static_cast<int>(ppb), y);
+  const dim3 grid(slabs, n);
+#define CA_GN(S, U)                                                                                                 \
+  gn_apply_kernel<S, U><<<grid, threads, 0, stream>>>(x0, c0, x1, c1, h, w, imgs_per_sample, groups, eps, sums, gamma, \
+                                                      beta, static_cast<int>(ppb), y)
+  if (silu) {
+    if (up2x) CA_GN(true, true); else CA_GN(true, false);
+  } else {
+    if (up2x) CA_GN(false, true); else CA_GN(false, false);
+  }
+#undef CA_GN
   return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, the row is held in registers (NV 16-byte vectors per lane): one global read,
-// two-pass mean / variance from registers, one write.  Optional fused pre-add of a broadcast row vector
-// (frame position embedding / single-token cross-attention output).
+// two-pass mean / variance from registers, one write.  The kernel is instruction-issue bound next to the HBM rate
+// (40 elements per lane at C = 1280), so the arithmetic runs on packed fp32x2 (FADD2 / FFMA2 / FMUL2).
+// RV: fused pre-add of a broadcast row vector (frame position embedding / single-token cross-attention output),
+// rounded to bf16 like the eager add it replaces; optionally also written out (y_sum).
 // ---------------------------------------------------------------------------------------------
-template <int NV>
-__global__ void __launch_bounds__(256)
+template <int NV, bool RV>
+__global__ void __launch_bounds__(256, (NV <= 5) ? 5 : 3)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, float eps,
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  const __nv_bfloat16* __restrict__ add_rowvec, long long rows_per_vec,
@@ -223,51 +241,58 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
   const int lane = threadIdx.x & 31;
   const int nvec = c >> 3;
   const __nv_bfloat16* xr = x + row * c;
-  const __nv_bfloat16* av = add_rowvec ? add_rowvec + (row / rows_per_vec) * c : nullptr;
   uint4 u[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int v = lane + 32 * k;
     if (v < nvec) u[k] = ld_nc(xr + v * 8);
   }
-  float f[NV][8];
-  float s = 0.f;
+  // The row stays PACKED (bf16 pairs, NV*4 registers) and is widened again in each of the three passes: the kernel
+  // is bound by bytes in flight per SM, i.e. by occupancy, so registers are worth more than the extra shifts.
+  auto widen = [](uint32_t w) { return pack_f32x2(bf16lo_to_float(w), bf16hi_to_float(w)); };
+  uint64_t s2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int v = lane + 32 * k;
     if (v < nvec) {
-      const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&u[k]);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[k][e] = __bfloat162float(hv[e]);
-      if (av) {
-        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(av + v * 8));
-        const __nv_bfloat16* ha = reinterpret_cast<const __nv_bfloat16*>(&ua);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[k][e] = round_bf16(f[k][e] + __bfloat162float(ha[e]));
-        if (y_sum) {
-          *reinterpret_cast<uint4*>(y_sum + row * c + v * 8) =
-              make_uint4(pack_bf16x2(f[k][0], f[k][1]), pack_bf16x2(f[k][2], f[k][3]), pack_bf16x2(f[k][4], f[k][5]),
-                         pack_bf16x2(f[k][6], f[k][7]));
-        }
+      if constexpr (RV) {
+        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(add_rowvec + (row / rows_per_vec) * c + v * 8));
+        u[k].x = add_bf16x2(u[k].x, ua.x);  // bf16(x + rowvec), one rounding
+        u[k].y = add_bf16x2(u[k].y, ua.y);
+        u[k].z = add_bf16x2(u[k].z, ua.z);
+        u[k].w = add_bf16x2(u[k].w, ua.w);
+        if (y_sum) *reinterpret_cast<uint4*>(y_sum + row * c + v * 8) = u[k];
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s += f[k][e];
+      s2 = add_f32x2(add_f32x2(s2, widen(u[k].x)), widen(u[k].y));
+      s2 = add_f32x2(add_f32x2(s2, widen(u[k].z)), widen(u[k].w));
     }
   }
+  float s_lo, s_hi;
+  unpack_f32x2(s2, s_lo, s_hi);
+  float s = s_lo + s_hi;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / c;
-  float ss = 0.f;
+  const uint64_t nmean2 = pack_f32x2(-mean, -mean);
+  uint64_t ss2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     if (lane + 32 * k < nvec) {
+      const uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const float d = f[k][e] - mean; ss = fmaf(d, d, ss); }
+      for (int e = 0; e < 4; ++e) {
+        const uint64_t d = add_f32x2(widen(wds[e]), nmean2);
+        ss2 = fma_f32x2(d, d, ss2);
+      }
     }
   }
+  float ss_lo, ss_hi;
+  unpack_f32x2(ss2, ss_lo, ss_hi);
+  float ss = ss_lo + ss_hi;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float rstd = rsqrtf(ss / c + eps);
+  const uint64_t rstd2 = pack_f32x2(rstd, rstd);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int v = lane + 32 * k;
@@ -276,13 +301,21 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o[8];
+      const uint64_t gg[4] = {pack_f32x2(g0.x, g0.y), pack_f32x2(g0.z, g0.w), pack_f32x2(g1.x, g1.y),
+                              pack_f32x2(g1.z, g1.w)};
+      const uint64_t bb[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y),
+                              pack_f32x2(b1.z, b1.w)};
+      const uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      uint32_t o[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = (f[k][e] - mean) * rstd * gg[e] + bb[e];
-      *reinterpret_cast<uint4*>(y + row * c + v * 8) =
-          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      for (int e = 0; e < 4; ++e) {
+        // ((x - mean) * rstd) * gamma + beta, the association of the eager kernel
+        const uint64_t r = fma_f32x2(mul_f32x2(add_f32x2(widen(wds[e]), nmean2), rstd2), gg[e], bb[e]);
+        float r0, r1;
+        unpack_f32x2(r, r0, r1);
+        o[e] = pack_bf16x2(r0, r1);
+      }
+      *reinterpret_cast<uint4*>(y + row * c + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -295,7 +328,13 @@ cudaError_t launch_layernorm(const __nv_bfloat16* x, long long rows, int c, floa
   const unsigned blocks = static_cast<unsigned>((rows + warps - 1) / warps);
   const long long rpv = rows_per_vec > 0 ? rows_per_vec : 1;
   const int nv = ((c >> 3) + 31) / 32;
-#define CA_LN(NV) layernorm_kernel<NV><<<blocks, warps * 32, 0, stream>>>(x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y)
+#define CA_LN(NV)                                                                                                      \
+  do {                                                                                                                 \
+    if (add_rowvec != nullptr)                                                                                         \
+      layernorm_kernel<NV, true><<<blocks, warps * 32, 0, stream>>>(x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y); \
+    else                                                                                                               \
+      layernorm_kernel<NV, false><<<blocks, warps * 32, 0, stream>>>(x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y); \
+  } while (0)
   switch (nv) {
     case 1: CA_LN(1); break;
     case 2: CA_LN(2); break;
