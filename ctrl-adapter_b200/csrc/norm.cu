@@ -241,6 +241,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
   const int lane = threadIdx.x & 31;
   const int nvec = c >> 3;
   const __nv_bfloat16* xr = x + row * c;
+  [[maybe_unused]] const __nv_bfloat16* av = RV ? add_rowvec + (row / rows_per_vec) * c : nullptr;
   uint4 u[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -256,7 +257,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
     const int v = lane + 32 * k;
     if (v < nvec) {
       if constexpr (RV) {
-        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(add_rowvec + (row / rows_per_vec) * c + v * 8));
+        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(av + v * 8));
         u[k].x = add_bf16x2(u[k].x, ua.x);  // bf16(x + rowvec), one rounding
         u[k].y = add_bf16x2(u[k].y, ua.y);
         u[k].z = add_bf16x2(u[k].z, ua.z);

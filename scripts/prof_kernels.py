@@ -50,6 +50,16 @@ elif which.startswith("conv"):  # conv or conv:<bn>
     bias = torch.zeros(320, device=dev)
     fn = lambda: ops.conv2d(x, w, bias, bn=bn)  # noqa: E731
     flops = 2.0 * 16 * 128 * 128 * 2880 * 320
+elif which == "ln":
+    x = rnd(16384, 1280)
+    g, b = torch.ones(1280, device=dev), torch.zeros(1280, device=dev)
+    fn = lambda: ops.layer_norm(x, g, b)  # noqa: E731
+    flops = 0.0
+elif which == "gn":
+    x = rnd(16, 128, 128, 320)
+    g, b = torch.ones(320, device=dev), torch.zeros(320, device=dev)
+    fn = lambda: ops.group_norm(x, g, b, 1e-5, silu=True)  # noqa: E731
+    flops = 0.0
 else:
     raise SystemExit(which)
 
