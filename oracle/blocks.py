@@ -1070,3 +1070,299 @@ def get_up_block_3d(up_block_type, num_layers, in_channels, out_channels, prev_o
                                   use_linear_projection=use_linear_projection,
                                   only_cross_attention=only_cross_attention, upcast_attention=upcast_attention)
     raise ValueError(f"{up_block_type} does not exist.")
+
+
+# ------------------------------------------------------------------------------------------------
+# Spatio-temporal (Stable Video Diffusion) blocks: diffusers v0.27.2 models/resnet.py::SpatioTemporalResBlock,
+# models/transformers/transformer_temporal.py::TransformerSpatioTemporalModel and the *SpatioTemporal blocks of
+# models/unets/unet_3d_blocks.py, reached from svd/models/unets/unet_spatio_temporal_condition.py:13,168-235.
+# Restated from the published v0.27.2 semantics (diffusers is not vendored by the reference): parity unpinned for this
+# layer, like the rest of this file.  The eps defaults below are the class defaults of that release -- get_down_block /
+# get_up_block do NOT forward the resnet_eps the UNet passes (unet_spatio_temporal_condition.py:176, 229).
+# ------------------------------------------------------------------------------------------------
+class SpatioTemporalResBlock(nn.Module):
+    def __init__(self, in_channels: int, out_channels: Optional[int] = None, temb_channels: int = 512, eps: float = 1e-6,
+                 temporal_eps: Optional[float] = None, merge_factor: float = 0.5,
+                 merge_strategy: str = "learned_with_images", switch_spatial_to_temporal_mix: bool = False):
+        super().__init__()
+        self.spatial_res_block = ResnetBlock2D(in_channels=in_channels, out_channels=out_channels,
+                                               temb_channels=temb_channels, eps=eps)
+        mid = out_channels if out_channels is not None else in_channels
+        self.temporal_res_block = TemporalResnetBlock(in_channels=mid, out_channels=mid, temb_channels=temb_channels,
+                                                      eps=temporal_eps if temporal_eps is not None else eps)
+        self.time_mixer = AlphaBlender(alpha=merge_factor, merge_strategy=merge_strategy,
+                                       switch_spatial_to_temporal_mix=switch_spatial_to_temporal_mix)
+
+    def forward(self, hidden_states, temb=None, image_only_indicator=None):
+        num_frames = image_only_indicator.shape[-1]
+        hidden_states = self.spatial_res_block(hidden_states, temb)
+        batch_frames, channels, height, width = hidden_states.shape
+        batch_size = batch_frames // num_frames
+        hidden_states_mix = (hidden_states[None, :].reshape(batch_size, num_frames, channels, height, width)
+                             .permute(0, 2, 1, 3, 4))
+        hidden_states = (hidden_states[None, :].reshape(batch_size, num_frames, channels, height, width)
+                         .permute(0, 2, 1, 3, 4))
+        if temb is not None:
+            temb = temb.reshape(batch_size, num_frames, -1)
+        hidden_states = self.temporal_res_block(hidden_states, temb)
+        hidden_states = self.time_mixer(x_spatial=hidden_states_mix, x_temporal=hidden_states,
+                                        image_only_indicator=image_only_indicator)
+        return hidden_states.permute(0, 2, 1, 3, 4).reshape(batch_frames, channels, height, width)
+
+
+class TransformerSpatioTemporalModel(nn.Module):
+    def __init__(self, num_attention_heads: int = 16, attention_head_dim: int = 88, in_channels: int = 320,
+                 out_channels: Optional[int] = None, num_layers: int = 1, cross_attention_dim: Optional[int] = None):
+        super().__init__()
+        self.num_attention_heads = num_attention_heads
+        self.attention_head_dim = attention_head_dim
+        inner_dim = num_attention_heads * attention_head_dim
+        self.inner_dim = inner_dim
+        self.in_channels = in_channels
+        self.norm = nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6)
+        self.proj_in = nn.Linear(in_channels, inner_dim)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(inner_dim, num_attention_heads, attention_head_dim, cross_attention_dim=cross_attention_dim)
+            for _ in range(num_layers)])
+        self.temporal_transformer_blocks = nn.ModuleList([
+            TemporalBasicTransformerBlock(inner_dim, inner_dim, num_attention_heads, attention_head_dim,
+                                          cross_attention_dim=cross_attention_dim)
+            for _ in range(num_layers)])
+        time_embed_dim = in_channels * 4
+        self.time_pos_embed = TimestepEmbedding(in_channels, time_embed_dim, out_dim=in_channels)
+        self.time_proj = Timesteps(in_channels, True, 0)
+        self.time_mixer = AlphaBlender(alpha=0.5, merge_strategy="learned_with_images")
+        self.out_channels = in_channels if out_channels is None else out_channels
+        self.proj_out = nn.Linear(inner_dim, in_channels)
+
+    def forward(self, hidden_states, encoder_hidden_states=None, image_only_indicator=None, return_dict: bool = False):
+        batch_frames, _, height, width = hidden_states.shape
+        num_frames = image_only_indicator.shape[-1]
+        batch_size = batch_frames // num_frames
+        time_context = encoder_hidden_states
+        time_context_first_timestep = time_context[None, :].reshape(batch_size, num_frames, -1, time_context.shape[-1])[:, 0]
+        time_context = time_context_first_timestep[None, :].broadcast_to(height * width, batch_size, 1, time_context.shape[-1])
+        time_context = time_context.reshape(height * width * batch_size, 1, time_context.shape[-1])
+
+        residual = hidden_states
+        hidden_states = self.norm(hidden_states)
+        inner_dim = hidden_states.shape[1]
+        hidden_states = hidden_states.permute(0, 2, 3, 1).reshape(batch_frames, height * width, inner_dim)
+        hidden_states = self.proj_in(hidden_states)
+
+        num_frames_emb = torch.arange(num_frames, device=hidden_states.device)
+        num_frames_emb = num_frames_emb.repeat(batch_size, 1).reshape(-1)
+        t_emb = self.time_proj(num_frames_emb).to(dtype=hidden_states.dtype)
+        emb = self.time_pos_embed(t_emb)[:, None, :]
+
+        for block, temporal_block in zip(self.transformer_blocks, self.temporal_transformer_blocks):
+            hidden_states = block(hidden_states, encoder_hidden_states=encoder_hidden_states)
+            hidden_states_mix = hidden_states + emb
+            hidden_states_mix = temporal_block(hidden_states_mix, num_frames=num_frames, encoder_hidden_states=time_context)
+            hidden_states = self.time_mixer(x_spatial=hidden_states, x_temporal=hidden_states_mix,
+                                            image_only_indicator=image_only_indicator)
+
+        hidden_states = self.proj_out(hidden_states)
+        hidden_states = hidden_states.reshape(batch_frames, height, width, inner_dim).permute(0, 3, 1, 2).contiguous()
+        output = hidden_states + residual
+        return (output,)
+
+
+class DownBlockSpatioTemporal(nn.Module):
+    has_cross_attention = False
+
+    def __init__(self, in_channels: int, out_channels: int, temb_channels: int, num_layers: int = 1,
+                 add_downsample: bool = True):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            SpatioTemporalResBlock(in_channels=in_channels if i == 0 else out_channels, out_channels=out_channels,
+                                   temb_channels=temb_channels, eps=1e-5)
+            for i in range(num_layers)])
+        self.downsamplers = (nn.ModuleList([Downsample2D(out_channels, use_conv=True, out_channels=out_channels, name="op")])
+                             if add_downsample else None)
+
+    def forward(self, hidden_states, temb=None, image_only_indicator=None):
+        output_states = ()
+        for resnet in self.resnets:
+            hidden_states = resnet(hidden_states, temb, image_only_indicator=image_only_indicator)
+            output_states = output_states + (hidden_states,)
+        if self.downsamplers is not None:
+            for downsampler in self.downsamplers:
+                hidden_states = downsampler(hidden_states)
+            output_states = output_states + (hidden_states,)
+        return hidden_states, output_states
+
+
+class CrossAttnDownBlockSpatioTemporal(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels: int, out_channels: int, temb_channels: int, num_layers: int = 1,
+                 transformer_layers_per_block=1, num_attention_heads: int = 1, cross_attention_dim: int = 1280,
+                 add_downsample: bool = True):
+        super().__init__()
+        self.num_attention_heads = num_attention_heads
+        tl = _as_list(transformer_layers_per_block, num_layers)
+        self.resnets = nn.ModuleList([
+            SpatioTemporalResBlock(in_channels=in_channels if i == 0 else out_channels, out_channels=out_channels,
+                                   temb_channels=temb_channels, eps=1e-6)
+            for i in range(num_layers)])
+        self.attentions = nn.ModuleList([
+            TransformerSpatioTemporalModel(num_attention_heads, out_channels // num_attention_heads,
+                                           in_channels=out_channels, num_layers=tl[i],
+                                           cross_attention_dim=cross_attention_dim)
+            for i in range(num_layers)])
+        self.downsamplers = (nn.ModuleList([Downsample2D(out_channels, use_conv=True, out_channels=out_channels,
+                                                         padding=1, name="op")]) if add_downsample else None)
+
+    def forward(self, hidden_states, temb=None, encoder_hidden_states=None, image_only_indicator=None):
+        output_states = ()
+        for resnet, attn in zip(self.resnets, self.attentions):
+            hidden_states = resnet(hidden_states, temb, image_only_indicator=image_only_indicator)
+            hidden_states = attn(hidden_states, encoder_hidden_states=encoder_hidden_states,
+                                 image_only_indicator=image_only_indicator, return_dict=False)[0]
+            output_states = output_states + (hidden_states,)
+        if self.downsamplers is not None:
+            for downsampler in self.downsamplers:
+                hidden_states = downsampler(hidden_states)
+            output_states = output_states + (hidden_states,)
+        return hidden_states, output_states
+
+
+class UNetMidBlockSpatioTemporal(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels: int, temb_channels: int, num_layers: int = 1, transformer_layers_per_block=1,
+                 num_attention_heads: int = 1, cross_attention_dim: int = 1280):
+        super().__init__()
+        self.num_attention_heads = num_attention_heads
+        tl = _as_list(transformer_layers_per_block, num_layers)
+        resnets = [SpatioTemporalResBlock(in_channels=in_channels, out_channels=in_channels, temb_channels=temb_channels,
+                                          eps=1e-5)]
+        attentions = []
+        for i in range(num_layers):
+            attentions.append(TransformerSpatioTemporalModel(num_attention_heads, in_channels // num_attention_heads,
+                                                             in_channels=in_channels, num_layers=tl[i],
+                                                             cross_attention_dim=cross_attention_dim))
+            resnets.append(SpatioTemporalResBlock(in_channels=in_channels, out_channels=in_channels,
+                                                  temb_channels=temb_channels, eps=1e-5))
+        self.attentions = nn.ModuleList(attentions)
+        self.resnets = nn.ModuleList(resnets)
+
+    def forward(self, hidden_states, temb=None, encoder_hidden_states=None, image_only_indicator=None):
+        hidden_states = self.resnets[0](hidden_states, temb, image_only_indicator=image_only_indicator)
+        for attn, resnet in zip(self.attentions, self.resnets[1:]):
+            hidden_states = attn(hidden_states, encoder_hidden_states=encoder_hidden_states,
+                                 image_only_indicator=image_only_indicator, return_dict=False)[0]
+            hidden_states = resnet(hidden_states, temb, image_only_indicator=image_only_indicator)
+        return hidden_states
+
+
+class UpBlockSpatioTemporal(nn.Module):
+    has_cross_attention = False
+
+    def __init__(self, in_channels: int, prev_output_channel: int, out_channels: int, temb_channels: int,
+                 resolution_idx: Optional[int] = None, num_layers: int = 1, resnet_eps: float = 1e-6,
+                 add_upsample: bool = True):
+        super().__init__()
+        resnets = []
+        for i in range(num_layers):
+            res_skip_channels = in_channels if (i == num_layers - 1) else out_channels
+            resnet_in_channels = prev_output_channel if i == 0 else out_channels
+            resnets.append(SpatioTemporalResBlock(in_channels=resnet_in_channels + res_skip_channels,
+                                                  out_channels=out_channels, temb_channels=temb_channels, eps=resnet_eps))
+        self.resnets = nn.ModuleList(resnets)
+        self.upsamplers = (nn.ModuleList([Upsample2D(out_channels, use_conv=True, out_channels=out_channels)])
+                           if add_upsample else None)
+        self.resolution_idx = resolution_idx
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb=None, image_only_indicator=None):
+        for resnet in self.resnets:
+            res_hidden_states = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = torch.cat([hidden_states, res_hidden_states], dim=1)
+            hidden_states = resnet(hidden_states, temb, image_only_indicator=image_only_indicator)
+        if self.upsamplers is not None:
+            for upsampler in self.upsamplers:
+                hidden_states = upsampler(hidden_states)
+        return hidden_states
+
+
+class CrossAttnUpBlockSpatioTemporal(nn.Module):
+    has_cross_attention = True
+
+    def __init__(self, in_channels: int, out_channels: int, prev_output_channel: int, temb_channels: int,
+                 resolution_idx: Optional[int] = None, num_layers: int = 1, transformer_layers_per_block=1,
+                 resnet_eps: float = 1e-6, num_attention_heads: int = 1, cross_attention_dim: int = 1280,
+                 add_upsample: bool = True):
+        super().__init__()
+        self.num_attention_heads = num_attention_heads
+        tl = _as_list(transformer_layers_per_block, num_layers)
+        resnets, attentions = [], []
+        for i in range(num_layers):
+            res_skip_channels = in_channels if (i == num_layers - 1) else out_channels
+            resnet_in_channels = prev_output_channel if i == 0 else out_channels
+            resnets.append(SpatioTemporalResBlock(in_channels=resnet_in_channels + res_skip_channels,
+                                                  out_channels=out_channels, temb_channels=temb_channels, eps=resnet_eps))
+            attentions.append(TransformerSpatioTemporalModel(num_attention_heads, out_channels // num_attention_heads,
+                                                             in_channels=out_channels, num_layers=tl[i],
+                                                             cross_attention_dim=cross_attention_dim))
+        self.attentions = nn.ModuleList(attentions)
+        self.resnets = nn.ModuleList(resnets)
+        self.upsamplers = (nn.ModuleList([Upsample2D(out_channels, use_conv=True, out_channels=out_channels)])
+                           if add_upsample else None)
+        self.resolution_idx = resolution_idx
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb=None, encoder_hidden_states=None,
+                image_only_indicator=None):
+        for resnet, attn in zip(self.resnets, self.attentions):
+            res_hidden_states = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = torch.cat([hidden_states, res_hidden_states], dim=1)
+            hidden_states = resnet(hidden_states, temb, image_only_indicator=image_only_indicator)
+            hidden_states = attn(hidden_states, encoder_hidden_states=encoder_hidden_states,
+                                 image_only_indicator=image_only_indicator, return_dict=False)[0]
+        if self.upsamplers is not None:
+            for upsampler in self.upsamplers:
+                hidden_states = upsampler(hidden_states)
+        return hidden_states
+
+
+_get_down_block_3d_base = get_down_block_3d
+_get_up_block_3d_base = get_up_block_3d
+
+
+def get_down_block_3d(down_block_type, num_layers, in_channels, out_channels, temb_channels, add_downsample,  # noqa: F811
+                      resnet_eps=None, transformer_layers_per_block=1, cross_attention_dim=None,
+                      num_attention_heads=None, **kw):
+    """unet_3d_blocks.get_down_block including the spatio-temporal (SVD) types, which ignore resnet_eps."""
+    if down_block_type == "DownBlockSpatioTemporal":
+        return DownBlockSpatioTemporal(num_layers=num_layers, in_channels=in_channels, out_channels=out_channels,
+                                       temb_channels=temb_channels, add_downsample=add_downsample)
+    if down_block_type == "CrossAttnDownBlockSpatioTemporal":
+        return CrossAttnDownBlockSpatioTemporal(in_channels=in_channels, out_channels=out_channels,
+                                                temb_channels=temb_channels, num_layers=num_layers,
+                                                transformer_layers_per_block=transformer_layers_per_block,
+                                                add_downsample=add_downsample, cross_attention_dim=cross_attention_dim,
+                                                num_attention_heads=num_attention_heads)
+    return _get_down_block_3d_base(down_block_type, num_layers, in_channels, out_channels, temb_channels, add_downsample,
+                                   resnet_eps, cross_attention_dim=cross_attention_dim,
+                                   num_attention_heads=num_attention_heads, **kw)
+
+
+def get_up_block_3d(up_block_type, num_layers, in_channels, out_channels, prev_output_channel, temb_channels,  # noqa: F811
+                    add_upsample, resnet_eps=None, transformer_layers_per_block=1, resolution_idx=None,
+                    cross_attention_dim=None, num_attention_heads=None, **kw):
+    if up_block_type == "UpBlockSpatioTemporal":
+        return UpBlockSpatioTemporal(num_layers=num_layers, in_channels=in_channels, out_channels=out_channels,
+                                     prev_output_channel=prev_output_channel, temb_channels=temb_channels,
+                                     resolution_idx=resolution_idx, add_upsample=add_upsample)
+    if up_block_type == "CrossAttnUpBlockSpatioTemporal":
+        return CrossAttnUpBlockSpatioTemporal(in_channels=in_channels, out_channels=out_channels,
+                                              prev_output_channel=prev_output_channel, temb_channels=temb_channels,
+                                              resolution_idx=resolution_idx, num_layers=num_layers,
+                                              transformer_layers_per_block=transformer_layers_per_block,
+                                              add_upsample=add_upsample, cross_attention_dim=cross_attention_dim,
+                                              num_attention_heads=num_attention_heads)
+    return _get_up_block_3d_base(up_block_type, num_layers, in_channels, out_channels, prev_output_channel, temb_channels,
+                                 add_upsample, resnet_eps, cross_attention_dim=cross_attention_dim,
+                                 num_attention_heads=num_attention_heads, **kw)

@@ -87,3 +87,50 @@ def unet_i2vgen_inputs(b: int = 1, f: int = 4, r: int = 16, seed: int = 0, with_
                 image_embeddings=seeded_tensor("i2v_image_embeddings", (b, 1, 1024), seed),
                 encoder_hidden_states=seeded_tensor("i2v_ehs", (b, 77, 1024), seed),
                 down_block_additional_residuals=res, mid_block_additional_residual=mid)
+
+
+# Reduced-width configurations of the two video UNets: same block types, depths and code paths as the released models
+# (block_out_channels 320/640/1280/1280), small enough that the REAL reference classes run on CPU in seconds when the
+# golden vectors are generated (tests/golden/make_golden.py) and checked (tests/test_oracle_golden.py).
+UNET_SVD_SMALL_KW = dict(in_channels=8, out_channels=4, block_out_channels=(64, 128, 256, 256),
+                         num_attention_heads=(2, 4, 4, 8), cross_attention_dim=96, addition_time_embed_dim=32,
+                         projection_class_embeddings_input_dim=96, layers_per_block=2, num_frames=4)
+UNET_I2VGEN_SMALL_KW = dict(in_channels=4, out_channels=4, block_out_channels=(64, 128, 256, 256), layers_per_block=2,
+                            norm_num_groups=32, cross_attention_dim=96, attention_head_dim=32)
+
+
+def unet_svd_inputs(b: int = 1, f: int = 4, r: int = 16, seed: int = 0, with_residuals: bool = True,
+                    chans=(64, 128, 256, 256), ctx: int = 96):
+    """SVD UNet inputs (svd/pipelines/svd_controlnet_adapter_pipeline.py call site): sample (b, f, 8, r, r), image
+    embedding (b, 1, ctx), added_time_ids (b, 3) = [fps - 1, motion bucket, noise aug]; the adapter residuals are passed
+    5-D ("b c f h w") with three surplus entries at the end (zip() truncation, quirk Q7) and a 5-D mid residual."""
+    res = mid = None
+    if with_residuals:
+        c0, c1, c2, c3 = chans
+        shapes = [(c0, 1), (c0, 1), (c0, 1), (c0, 2), (c1, 2), (c1, 2), (c1, 4), (c2, 4), (c2, 4), (c2, 8), (c3, 8),
+                  (c3, 8)]
+        res = [seeded_tensor(f"svd_res{i}", (b, c, f, r // d, r // d), seed, 0.5) for i, (c, d) in enumerate(shapes)]
+        res += [torch.zeros(b, c3, f, r // 8, r // 8)] * 3
+        mid = seeded_tensor("svd_mid", (b, c3, f, r // 8, r // 8), seed, 0.5)
+    return dict(sample=seeded_tensor("svd_sample", (b, f, 8, r, r), seed), timestep=torch.tensor(1.6377),
+                encoder_hidden_states=seeded_tensor("svd_ehs", (b, 1, ctx), seed),
+                added_time_ids=torch.tensor([[6.0, 127.0, 0.02]] * b),
+                down_block_additional_residuals=res, mid_block_additional_residual=mid)
+
+
+def unet_i2vgen_small_inputs(b: int = 1, f: int = 4, r: int = 16, seed: int = 0, with_residuals: bool = True,
+                             chans=(64, 128, 256, 256), ctx: int = 96):
+    """Inputs of the reduced-width I2VGen-XL UNet (UNET_I2VGEN_SMALL_KW); residuals 4-D (b f) c h w as the pipeline
+    passes them (i2vgen_xl/pipelines/...pipeline.py:1080-1082), 12 entries for 12 skip tensors."""
+    res = mid = None
+    c0, c1, c2, c3 = chans
+    if with_residuals:
+        shapes = [(c0, 1), (c0, 1), (c0, 1), (c0, 2), (c1, 2), (c1, 2), (c1, 4), (c2, 4), (c2, 4), (c2, 8), (c3, 8),
+                  (c3, 8)]
+        res = [seeded_tensor(f"i2vs_res{i}", (b * f, c, r // d, r // d), seed, 0.5) for i, (c, d) in enumerate(shapes)]
+        mid = seeded_tensor("i2vs_mid", (b * f, c3, r // 8, r // 8), seed, 0.5)
+    return dict(sample=seeded_tensor("i2vs_sample", (b, 4, f, r, r), seed), timestep=torch.tensor(961.0),
+                fps=torch.tensor([16.0] * b), image_latents=seeded_tensor("i2vs_image_latents", (b, 4, f, r, r), seed),
+                image_embeddings=seeded_tensor("i2vs_image_embeddings", (b, 1, ctx), seed),
+                encoder_hidden_states=seeded_tensor("i2vs_ehs", (b, 77, ctx), seed),
+                down_block_additional_residuals=res, mid_block_additional_residual=mid)

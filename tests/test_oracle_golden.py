@@ -119,3 +119,24 @@ def test_sdxl_unet_param_count_and_adapter_wiring():
         c = ControlNetModel(**cases.CONTROLNET_KW)
     assert sum(p.numel() for p in u.parameters()) == 2567463684
     assert sum(p.numel() for p in c.parameters()) == 361279120
+
+
+def test_unet_svd_matches_reference():
+    """Reduced-width SVD UNet (same block types / depths as the released model) incl. the reference's 5-D residual
+    injection with zip truncation and the mid residual (svd/.../unet_spatio_temporal_condition.py:457-471, 485-490)."""
+    from oracle.unet_svd import UNetSpatioTemporalConditionModel
+    u = seeded_init_(UNetSpatioTemporalConditionModel(**cases.UNET_SVD_SMALL_KW), seed=11).eval()
+    assert sum(p.numel() for p in u.parameters()) == GOLD["unet_svd_small"]["n_params"]
+    assert_fp(u(**cases.unet_svd_inputs(with_residuals=True))[0], GOLD["unet_svd_small"]["with_residuals"], rtol=2e-5, atol=2e-6)
+    assert_fp(u(**cases.unet_svd_inputs(with_residuals=False))[0], GOLD["unet_svd_small"]["plain"], rtol=2e-5, atol=2e-6)
+
+
+def test_unet_i2vgen_matches_reference():
+    """Reduced-width I2VGen-XL UNet incl. the residual injection (i2vgen_xl/.../unet_i2vgen_xl.py:681-695, 709-714)."""
+    from oracle.unet_i2vgen import I2VGenXLUNet
+    u = seeded_init_(I2VGenXLUNet(**cases.UNET_I2VGEN_SMALL_KW), seed=12).eval()
+    assert sum(p.numel() for p in u.parameters()) == GOLD["unet_i2vgen_small"]["n_params"]
+    assert_fp(u(**cases.unet_i2vgen_small_inputs(with_residuals=True))[0], GOLD["unet_i2vgen_small"]["with_residuals"],
+              rtol=2e-5, atol=2e-6)
+    assert_fp(u(**cases.unet_i2vgen_small_inputs(with_residuals=False))[0], GOLD["unet_i2vgen_small"]["plain"],
+              rtol=2e-5, atol=2e-6)
