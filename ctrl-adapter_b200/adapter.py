@@ -111,7 +111,8 @@ class TemporalBasicTransformerBlock(nn.Module):
 
     def forward(self, h, emb, frames: int, hw: int, ctx_vec, blend_src=None, blend_alpha=None):
         """h [B*F*HW, D]; emb [B*F, D] frame-position embedding added first (adapter_spatial_temporal.py:279);
-        ctx_vec [1, Dc]: single-token context (cross attention over one key collapses to to_out(to_v(ctx)))."""
+        ctx_vec [1, Dc] (or [B, Dc], one per clip): single-token context (cross attention over one key collapses to
+        to_out(to_v(ctx)))."""
         rows, d = h.shape
         clips = rows // (frames * hw)
         n_in, x = self.norm_in.layer_norm(h, add_rowvec=emb, rows_per_vec=hw, return_sum=True)
@@ -122,8 +123,19 @@ class TemporalBasicTransformerBlock(nn.Module):
         o = ops.temporal_attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], clips, frames, hw,
                                    self.heads, 0.125, row_stride=3 * inner)
         x = ops.linear(o, pk["wo"], pk["bo"], residual=x)
-        cv = self.attn2.single_token_output(ctx_vec)  # [1, D]
-        n3, x = self.norm3.layer_norm(x, add_rowvec=cv, rows_per_vec=rows, return_sum=True)
+        cv = self.attn2.single_token_output(ctx_vec)  # [1, D], or one row per clip ([B, D]: SVD backbone)
+        rpv = rows
+        if cv.shape[0] > 1:
+            # diffusers quirk kept by the reference (transformer_temporal.py / adapter_spatial_temporal.py:247-250):
+            # `time_context` is built in (pixel, clip) order but consumed by sequences in (clip, pixel) order, so the
+            # frame sequence of (clip b, pixel p) attends to the context of clip (b*hw + p) % B.  Distinct contexts only
+            # occur on the SVD path (CFG pair); the gather below is host-side glue over a [B, D] table.
+            if cv.shape[0] != clips:
+                raise ValueError("one context row per clip expected")
+            idx = torch.arange(clips * hw, device=cv.device) % clips
+            cv = cv[idx].reshape(clips, 1, hw, d).expand(clips, frames, hw, d).reshape(rows, d).contiguous()
+            rpv = 1
+        n3, x = self.norm3.layer_norm(x, add_rowvec=cv, rows_per_vec=rpv, return_sum=True)
         # NB diffusers applies norm2 before attn2 but with a single key the (normalised) query is irrelevant
         return self.ff(n3, residual=x, blend_src=blend_src, blend_alpha=blend_alpha)
 

@@ -1,0 +1,271 @@
+"""B200 host mirror of the Stable-Video-Diffusion UNet with the reference's residual injection
+(/root/reference/svd/models/unets/unet_spatio_temporal_condition.py: constructor :71-245, forward :357-526, injection
+:457-471 and :485-490; instantiated at inference.py:360, called at svd/pipelines/svd_controlnet_adapter_pipeline.py).
+
+Same state-dict keys as the reference class (stabilityai/stable-video-diffusion-img2vid[-xt] unet).  Everything runs on
+the kernels the adapter's video path already uses: frames stay in (clip, frame, pixel) token order, the temporal ResNet
+is a (3,1,1) multi-tap GEMM with 5-D GroupNorm statistics, the temporal transformer uses the frame-axis attention
+kernel, both AlphaBlender mixes are fused into the producing GEMM epilogue, and the skip concat of the up blocks is a
+second TMA source.  The conditioning of this backbone is ONE CLIP image token per clip, so every cross-attention
+collapses exactly to a per-clip broadcast vector to_out(to_v(ctx)) (same identity as the adapter's quirk Q5).
+
+STATUS: composed from building blocks that are GPU-validated through the adapter and I2VGen-XL paths; the composition
+itself is verified on CPU (tests/test_host_emulated_cpu.py: this module over an emulation of the op layer vs the restated
+reference class, which in turn is bit-exact against the reference's own class), but its GPU parity check
+(tests/test_zz_svd_gpu.py) has had no hardware run yet and reports xfail instead of red until it has.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from .adapter import (AlphaBlender, TemporalBasicTransformerBlock, TemporalResnetBlock, _ConfigDict, timestep_vector,
+                      to_channels_last_bf16)
+from .layers import BF16, BasicTransformerBlock, Conv2d, Linear, Norm, ResnetBlock2D, TimestepEmbedding
+
+
+class SpatioTemporalResBlock(nn.Module):
+    """diffusers SpatioTemporalResBlock: spatial ResnetBlock2D -> TemporalResnetBlock, blended by a learned alpha."""
+
+    def __init__(self, cin: int, cout: int, temb: int, eps: float):
+        super().__init__()
+        self.spatial_res_block = ResnetBlock2D(cin, cout, temb, eps)
+        self.temporal_res_block = TemporalResnetBlock(cout, temb, eps)
+        self.time_mixer = AlphaBlender(0.5)
+
+    def forward(self, x, temb_act, frames: int, x2=None):
+        s = self.spatial_res_block(x, temb_act, x2=x2)
+        return self.temporal_res_block(s, frames, temb_act, blend_src=s, blend_alpha=self.time_mixer.alpha())
+
+
+class TransformerSpatioTemporalModel(nn.Module):
+    """diffusers TransformerSpatioTemporalModel for a single-token context (the only form this backbone is driven with)."""
+
+    def __init__(self, heads: int, head_dim: int, in_channels: int, num_layers: int, cross_dim: int):
+        super().__init__()
+        if head_dim != 64:
+            raise NotImplementedError("attention_head_dim must be 64 (released SVD UNet)")
+        inner = heads * head_dim
+        self.in_channels, self.inner = in_channels, inner
+        self.norm = Norm(in_channels, 1e-6)
+        self.proj_in = Linear(in_channels, inner)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, heads, head_dim, cross_dim)
+                                                 for _ in range(num_layers)])
+        self.temporal_transformer_blocks = nn.ModuleList([TemporalBasicTransformerBlock(inner, heads, head_dim, cross_dim)
+                                                          for _ in range(num_layers)])
+        self.time_pos_embed = TimestepEmbedding(in_channels, in_channels * 4, out_dim=in_channels)
+        self.time_mixer = AlphaBlender(0.5)
+        self.proj_out = Linear(inner, in_channels)
+
+    def forward(self, x, ctx_vecs, frames: int):
+        """x [B*F, H, W, C]; ctx_vecs [B, Dc]: the clip's single context token (identical for all of its frames, which
+        is also what the temporal blocks use: `time_context` = the first frame's context, transformer_temporal.py)."""
+        n, h, w, c = x.shape
+        hw = h * w
+        clips = n // frames
+        tok = self.norm.group_norm(x, silu=False).reshape(n * hw, c)
+        hs = self.proj_in(tok)
+        frames_idx = torch.arange(frames, device=x.device, dtype=torch.float32).repeat(clips)
+        emb = self.time_pos_embed(ops.timestep_embedding(frames_idx, c))  # [B*F, C]; C == inner for this backbone
+        alpha = self.time_mixer.alpha()
+        for blk, tblk in zip(self.transformer_blocks, self.temporal_transformer_blocks):
+            h3 = hs.reshape(n, hw, self.inner)
+            h1 = blk.attn1(blk.norm1.layer_norm(h3), residual=h3).reshape(n * hw, self.inner)
+            cv = blk.attn2.single_token_output(ctx_vecs)  # [B, inner]
+            n3, hsum = blk.norm3.layer_norm(h1, add_rowvec=cv, rows_per_vec=frames * hw, return_sum=True)
+            hs = blk.ff(n3, residual=hsum)
+            hs = tblk(hs, emb, frames, hw, ctx_vecs, blend_src=hs, blend_alpha=alpha)
+        out = self.proj_out(hs, residual=x.reshape(n * hw, c))
+        return out.reshape(n, h, w, c)
+
+
+def _transformers(n, heads, c, depth, cross_dim):
+    return nn.ModuleList([TransformerSpatioTemporalModel(heads, c // heads, c, depth, cross_dim) for _ in range(n)])
+
+
+class _Down(nn.Module):
+    def __init__(self, cin, cout, temb, eps, heads, depth, cross_dim, add_downsample, cross_attn):
+        super().__init__()
+        self.has_cross_attention = cross_attn
+        self.resnets = nn.ModuleList([SpatioTemporalResBlock(cin if i == 0 else cout, cout, temb, eps) for i in range(2)])
+        if cross_attn:
+            self.attentions = _transformers(2, heads, cout, depth, cross_dim)
+        self.downsamplers = None
+        if add_downsample:
+            ds = nn.Module()
+            ds.conv = Conv2d(cout, cout, 3, stride=2)
+            self.downsamplers = nn.ModuleList([ds])
+
+    def forward(self, x, temb_act, ctx_vecs, frames):
+        outs = []
+        for i, r in enumerate(self.resnets):
+            x = r(x, temb_act, frames)
+            if self.has_cross_attention:
+                x = self.attentions[i](x, ctx_vecs, frames)
+            outs.append(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0].conv(x)
+            outs.append(x)
+        return x, outs
+
+
+class _Mid(nn.Module):
+    def __init__(self, c, temb, heads, depth, cross_dim):
+        super().__init__()
+        self.resnets = nn.ModuleList([SpatioTemporalResBlock(c, c, temb, 1e-5), SpatioTemporalResBlock(c, c, temb, 1e-5)])
+        self.attentions = _transformers(1, heads, c, depth, cross_dim)
+
+    def forward(self, x, temb_act, ctx_vecs, frames):
+        x = self.resnets[0](x, temb_act, frames)
+        x = self.attentions[0](x, ctx_vecs, frames)
+        return self.resnets[1](x, temb_act, frames)
+
+
+class _Up(nn.Module):
+    def __init__(self, cin, cout, prev, temb, eps, heads, depth, cross_dim, add_upsample, cross_attn):
+        super().__init__()
+        self.has_cross_attention = cross_attn
+        rs = []
+        for i in range(3):
+            skip_c = cin if i == 2 else cout
+            in_c = prev if i == 0 else cout
+            rs.append(SpatioTemporalResBlock(in_c + skip_c, cout, temb, eps))
+        self.resnets = nn.ModuleList(rs)
+        if cross_attn:
+            self.attentions = _transformers(3, heads, cout, depth, cross_dim)
+        self.upsamplers = None
+        if add_upsample:
+            us = nn.Module()
+            us.conv = Conv2d(cout, cout, 3)
+            self.upsamplers = nn.ModuleList([us])
+
+    def forward(self, x, skips, temb_act, ctx_vecs, frames):
+        for i, r in enumerate(self.resnets):
+            x = r(x, temb_act, frames, x2=skips.pop())
+            if self.has_cross_attention:
+                x = self.attentions[i](x, ctx_vecs, frames)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0].conv(ops.upsample2x(x))
+        return x
+
+
+class UNetSpatioTemporalConditionModel(nn.Module):
+    def __init__(self, sample_size=None, in_channels: int = 8, out_channels: int = 4,
+                 down_block_types=("CrossAttnDownBlockSpatioTemporal", "CrossAttnDownBlockSpatioTemporal",
+                                   "CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal"),
+                 up_block_types=("UpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal",
+                                 "CrossAttnUpBlockSpatioTemporal", "CrossAttnUpBlockSpatioTemporal"),
+                 block_out_channels=(320, 640, 1280, 1280), addition_time_embed_dim: int = 256,
+                 projection_class_embeddings_input_dim: int = 768, layers_per_block=2, cross_attention_dim=1024,
+                 transformer_layers_per_block=1, num_attention_heads=(5, 10, 10, 20), num_frames: int = 25):
+        super().__init__()
+        if len(down_block_types) != len(up_block_types) or len(block_out_channels) != len(down_block_types):
+            raise ValueError("Must provide the same number of `down_block_types`, `up_block_types` and "
+                             "`block_out_channels`")  # unet_spatio_temporal_condition.py:103-112
+        heads = (num_attention_heads,) * 4 if isinstance(num_attention_heads, int) else tuple(num_attention_heads)
+        if (tuple(block_out_channels) != (320, 640, 1280, 1280) or layers_per_block != 2
+                or transformer_layers_per_block != 1
+                or tuple(down_block_types) != ("CrossAttnDownBlockSpatioTemporal",) * 3 + ("DownBlockSpatioTemporal",)):
+            raise NotImplementedError("only the released SVD UNet topology is implemented")
+        if any(c // h != 64 for c, h in zip(block_out_channels, heads)):
+            # the checkpoints' config.json has num_attention_heads = [5, 10, 20, 20] (head dim 64 everywhere); the class
+            # default (5, 10, 10, 20) would give the third stage 128-wide heads, which the frame-axis kernel does not do
+            raise NotImplementedError("attention head dim must be 64: pass num_attention_heads=(5, 10, 20, 20) as the "
+                                      "released stable-video-diffusion configs do")
+        self.config = _ConfigDict(in_channels=in_channels, out_channels=out_channels, num_frames=num_frames,
+                                  sample_size=sample_size, block_out_channels=tuple(block_out_channels),
+                                  cross_attention_dim=cross_attention_dim,
+                                  addition_time_embed_dim=addition_time_embed_dim,
+                                  projection_class_embeddings_input_dim=projection_class_embeddings_input_dim)
+        c0, c1, c2, c3 = block_out_channels
+        temb = c0 * 4
+        xd = cross_attention_dim
+        self.conv_in = Conv2d(in_channels, c0, 3)
+        self.time_embedding = TimestepEmbedding(c0, temb)
+        self.add_embedding = TimestepEmbedding(projection_class_embeddings_input_dim, temb)
+        # class-default eps of diffusers v0.27.2 (get_down_block / get_up_block do not forward resnet_eps to these types)
+        h0, h1, h2, h3 = heads
+        self.down_blocks = nn.ModuleList([
+            _Down(c0, c0, temb, 1e-6, h0, 1, xd, True, True),
+            _Down(c0, c1, temb, 1e-6, h1, 1, xd, True, True),
+            _Down(c1, c2, temb, 1e-6, h2, 1, xd, True, True),
+            _Down(c2, c3, temb, 1e-5, h3, 1, xd, False, False)])
+        self.mid_block = _Mid(c3, temb, h3, 1, xd)
+        self.up_blocks = nn.ModuleList([
+            _Up(c2, c3, c3, temb, 1e-6, h3, 1, xd, True, False),
+            _Up(c1, c2, c3, temb, 1e-6, h2, 1, xd, True, True),
+            _Up(c0, c1, c2, temb, 1e-6, h1, 1, xd, True, True),
+            _Up(c0, c0, c1, temb, 1e-6, h0, 1, xd, False, True)])
+        self.conv_norm_out = Norm(c0, 1e-5)
+        self.conv_out = Conv2d(c0, out_channels, 3)
+        self._conv_out_pad = None
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _conv_out_packed(self):
+        """conv_out has 4 output channels; the kernel stores 16-byte vectors, so its weight rows are zero padded to 8."""
+        key = self.conv_out._key()
+        if self._conv_out_pad is None or self._conv_out_pad[0] != key:
+            w, b = self.conv_out.packed()
+            co = w.shape[0]
+            cp = (co + 7) // 8 * 8
+            wp = torch.zeros((cp, w.shape[1]), device=w.device, dtype=w.dtype)
+            wp[:co] = w
+            bp = torch.zeros(cp, device=w.device, dtype=torch.float32)
+            bp[:co] = b
+            self._conv_out_pad = (key, wp, bp)
+        return self._conv_out_pad[1], self._conv_out_pad[2]
+
+    @staticmethod
+    def _flatten_frames(r: torch.Tensor) -> torch.Tensor:
+        """5-D "b c f h w" residual -> (b f) c h w (unet_spatio_temporal_condition.py:459, 487)."""
+        return r.permute(0, 2, 1, 3, 4).flatten(0, 1) if r.dim() == 5 else r
+
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, added_time_ids, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, return_dict: bool = False):
+        if sample.dim() != 5:
+            raise ValueError("sample must be (batch, frames, channels, height, width)")
+        b, f = sample.shape[:2]
+        dev = sample.device
+        if sample.shape[-1] % 8 != 0 or sample.shape[-2] % 8 != 0:
+            raise NotImplementedError("latent resolution must be a multiple of 8")
+        if encoder_hidden_states.shape[1] != 1:
+            raise NotImplementedError("the SVD backbone is driven with one image-embedding token per clip")
+        # 1. time: one timestep for the whole batch (:393-406) + per-sample added_time_ids embedding (:414-418)
+        t = timestep_vector(timestep, b, dev)[:1].contiguous()
+        t_emb = self.time_embedding(ops.timestep_embedding(t, 320))  # [1, 1280]
+        ids = added_time_ids.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        tid = ops.timestep_embedding(ids, self.config.addition_time_embed_dim).reshape(b, -1).contiguous()
+        aug = self.add_embedding(tid)
+        emb = ops.add(t_emb.expand(b, -1).contiguous(), aug)  # [B, 1280]
+        temb_act = ops.silu(emb).repeat_interleave(f, dim=0).contiguous()  # one row per frame-image (:427)
+        ctx_vecs = encoder_hidden_states.to(BF16).reshape(b, -1).contiguous()  # [B, Dc]; every frame shares it (:430)
+
+        # 2. flatten frames, conv_in
+        x = self.conv_in(to_channels_last_bf16(sample.flatten(0, 1), 8))
+        skips = [x]
+        for blk in self.down_blocks:
+            x, outs = blk(x, temb_act, ctx_vecs, f)
+            skips += outs
+        if down_block_additional_residuals is not None:  # zip() truncation to the shorter list (:463-468)
+            for i, (s, r) in enumerate(zip(skips, down_block_additional_residuals)):
+                skips[i] = ops.add(s, to_channels_last_bf16(self._flatten_frames(r)))
+        x = self.mid_block(x, temb_act, ctx_vecs, f)
+        if isinstance(mid_block_additional_residual, torch.Tensor):
+            x = ops.add(x, to_channels_last_bf16(self._flatten_frames(mid_block_additional_residual)))
+        for blk in self.up_blocks:
+            x = blk(x, skips, temb_act, ctx_vecs, f)
+        h = self.conv_norm_out.group_norm(x, silu=True)
+        w, bias = self._conv_out_packed()
+        y = ops.conv2d(h, w, bias, ksize=3)
+        out = ops.nhwc_to_nchw(y, self.config.out_channels)  # [B*F, 4, H, W]
+        out = out.reshape(b, f, *out.shape[1:])
+        return (out,)

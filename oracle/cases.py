@@ -95,6 +95,8 @@ def unet_i2vgen_inputs(b: int = 1, f: int = 4, r: int = 16, seed: int = 0, with_
 UNET_SVD_SMALL_KW = dict(in_channels=8, out_channels=4, block_out_channels=(64, 128, 256, 256),
                          num_attention_heads=(2, 4, 4, 8), cross_attention_dim=96, addition_time_embed_dim=32,
                          projection_class_embeddings_input_dim=96, layers_per_block=2, num_frames=4)
+# released stable-video-diffusion-img2vid unet config.json (the reference class default has heads (5, 10, 10, 20))
+UNET_SVD_KW = dict(num_attention_heads=(5, 10, 20, 20), num_frames=14)
 UNET_I2VGEN_SMALL_KW = dict(in_channels=4, out_channels=4, block_out_channels=(64, 128, 256, 256), layers_per_block=2,
                             norm_num_groups=32, cross_attention_dim=96, attention_head_dim=32)
 

@@ -191,6 +191,25 @@ def check_unet_i2vgen(b=1, f=4, r=32, with_residuals=True):
                     tol_rel=3e-2, tol_max=8e-2)
 
 
+def check_unet_svd(b=2, f=4, r=32, with_residuals=True):
+    """SVD UNet at the released width (config.json heads 5/10/20/20), two clips with different image tokens (exercises the
+    per-clip broadcast form of the single-token cross attention), 5-D residuals with three surplus entries + mid."""
+    from ctrl_adapter_b200.unet_svd import UNetSpatioTemporalConditionModel
+    from oracle import cases
+    from oracle.unet_svd import UNetSpatioTemporalConditionModel as OUNet
+    inputs = cases.unet_svd_inputs(b, f, r, with_residuals=with_residuals, chans=(320, 640, 1280, 1280), ctx=1024)
+    call = lambda m, i: m(**i)  # noqa: E731
+    sd, ref, eager, inp16 = _oracle_runs(lambda: OUNet(**cases.UNET_SVD_KW), 8, inputs, call)
+    with torch.device("cuda"):
+        ours_m = UNetSpatioTemporalConditionModel(**cases.UNET_SVD_KW)
+    ours_m.load_state_dict(sd)
+    ours_m = ours_m.to(BF16).cuda().eval()
+    ours = ours_m(**inp16)
+    torch.cuda.synchronize()
+    return _compare(f"UNetSpatioTemporalConditionModel[svd] b={b} f={f} r={r} residuals={int(with_residuals)}", ours, ref,
+                    eager, tol_rel=3e-2, tol_max=8e-2)
+
+
 def _build_pair(make_oracle, make_ours, seed):
     """oracle (fp32, bf16-quantised weights, on GPU) and our module with identical weights."""
     from oracle.weights import seeded_init_
@@ -299,6 +318,7 @@ GROUPS = {
     "controlnet": [lambda: check_controlnet(2, 8), lambda: check_controlnet(2, 16, True, 0.75)],
     "unet": [lambda: check_unet_sdxl(2, 16, True), lambda: check_unet_sdxl(1, 32, False)],
     "video": [lambda: check_unet_i2vgen(1, 4, 32, True), lambda: check_unet_i2vgen(2, 2, 32, False)],
+    "svd": [lambda: check_unet_svd(2, 4, 32, True), lambda: check_unet_svd(1, 3, 16, False)],
     "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
 }
 

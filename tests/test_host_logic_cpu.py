@@ -67,6 +67,34 @@ def test_controlnet_and_unet_state_dicts_match_reference_layout():
             assert all(a[k].shape == b[k].shape for k in a)
 
 
+def test_video_unet_state_dicts_match_reference_layout():
+    """I2VGen-XL and SVD UNets: same keys / shapes as the (oracle restatement of the) reference classes, and the published
+    parameter count of the SVD UNet (1 524 623 082 for stable-video-diffusion-img2vid)."""
+    from ctrl_adapter_b200.unet_i2vgen import I2VGenXLUNet
+    from ctrl_adapter_b200.unet_svd import UNetSpatioTemporalConditionModel
+    from oracle.unet_i2vgen import I2VGenXLUNet as OI
+    from oracle.unet_svd import UNetSpatioTemporalConditionModel as OS
+    with torch.device("meta"):
+        for ours, ref in ((I2VGenXLUNet(), OI()),
+                          (UNetSpatioTemporalConditionModel(**cases.UNET_SVD_KW), OS(**cases.UNET_SVD_KW))):
+            a, b = ours.state_dict(), ref.state_dict()
+            assert set(a) == set(b), (sorted(set(a) - set(b))[:5], sorted(set(b) - set(a))[:5])
+            assert all(a[k].shape == b[k].shape for k in a), [k for k in a if a[k].shape != b[k].shape][:5]
+        n_svd = sum(p.numel() for p in ref.parameters())
+    assert n_svd == 1_524_623_082
+
+
+def test_svd_unet_rejects_unsupported_topologies():
+    from ctrl_adapter_b200.unet_svd import UNetSpatioTemporalConditionModel
+    with torch.device("meta"):
+        with pytest.raises(ValueError):
+            UNetSpatioTemporalConditionModel(down_block_types=("DownBlockSpatioTemporal",) * 3)
+        with pytest.raises(NotImplementedError):
+            UNetSpatioTemporalConditionModel(block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4))
+        with pytest.raises(NotImplementedError):
+            UNetSpatioTemporalConditionModel()  # class default heads (5, 10, 10, 20): 128-wide heads in stage 3
+
+
 def test_router_state_dict_and_config():
     from oracle.adapter import ControlNetRouter as O
     ours, ref = A.ControlNetRouter(**cases.ROUTER_KW), O(**cases.ROUTER_KW)
