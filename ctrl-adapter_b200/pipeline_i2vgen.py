@@ -24,12 +24,15 @@ class I2VGenXLControlNetAdapterLoop:
     def __init__(self, controlnet, adapter, unet, router=None, *, num_inference_steps: int = 50,
                  guidance_scale: float = 9.0, controlnet_conditioning_scale: float = 1.0,
                  inference_expert_masks: Optional[List[bool]] = None, skip_conv_in: bool = False,
-                 skip_time_emb: bool = False):
+                 skip_time_emb: bool = False, sparse_frames: Optional[List[int]] = None):
         self.controlnet, self.adapter, self.unet, self.router = controlnet, adapter, unet, router
         self.guidance_scale = float(guidance_scale)
         self.cond_scale = float(controlnet_conditioning_scale)
         self.masks = inference_expert_masks
         self.skip_conv_in, self.skip_time_emb = skip_conv_in, skip_time_emb
+        # sparse control (:1024-1033, :1053-1073): only these key frames of every clip go through the adapter; the other
+        # frames get zero residuals
+        self.sparse_frames = None if sparse_frames is None else [int(k) for k in sparse_frames]
         self.schedule = DDIMSchedule(num_inference_steps)
         self.num_inference_steps = num_inference_steps
         self._graph = None
@@ -62,6 +65,11 @@ class I2VGenXLControlNetAdapterLoop:
         self.unet._cond_cache = (tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in
                                        (self.fps, self.image_latents, self.image_embeddings, self.prompt_embeds)),
                                  self.unet_cond)
+        self._sparse_rows = None
+        if self.sparse_frames is not None:
+            if not all(0 <= k < f for k in self.sparse_frames):
+                raise ValueError("sparse_frames must index frames of the clip")
+            self._sparse_rows = torch.tensor([bb * f + k for bb in range(2 * b) for k in self.sparse_frames], device=dev)
         self._graph = None
         self.step_index = 0
 
@@ -87,8 +95,27 @@ class I2VGenXLControlNetAdapterLoop:
             from .adapter import as_nchw
             down = [as_nchw(d) for d in down]
             mid = as_nchw(mid) if mid is not None else None
-        down_a, mid_a = self.adapter(down, mid_block_res_sample=mid, sparsity_masking=None, num_frames=f, timestep=t,
-                                     encoder_hidden_states=self.adapter_ctx)
+        if self._sparse_rows is None:
+            down_a, mid_a = self.adapter(down, mid_block_res_sample=mid, sparsity_masking=None, num_frames=f, timestep=t,
+                                         encoder_hidden_states=self.adapter_ctx)
+        else:
+            # key-frame gather -> adapter on len(sparse_frames) frames per clip -> scatter into zero residuals
+            # (host-side index glue over ControlNet-sized tensors; the reference's dense tensors are fp32 zeros, which
+            # only changes where the skip + residual sum is rounded -- quirk Q21)
+            rows = self._sparse_rows
+            down_s = [d.index_select(0, rows) for d in down]
+            mid_s = mid.index_select(0, rows) if mid is not None else None
+            down_k, mid_k = self.adapter(down_s, mid_block_res_sample=mid_s, sparsity_masking=self.sparse_frames,
+                                         num_frames=len(self.sparse_frames), timestep=t,
+                                         encoder_hidden_states=self.adapter_ctx)
+
+            def densify(x):
+                full = torch.zeros((n, *x.shape[1:]), device=x.device, dtype=x.dtype).contiguous(
+                    memory_format=torch.channels_last)
+                full.index_copy_(0, rows, x)
+                return full
+            down_a = [densify(d) for d in down_k]
+            mid_a = densify(mid_k) if mid_k is not None else None
         residuals = None if self.cond_scale == 0 else down_a                     # mid is still injected (quirk Q9)
         sample = lat2.permute(0, 2, 1, 3, 4)                                     # (2B, 4, F, h, w) view
         eps = self.unet(sample, t, self.fps, self.image_latents, image_embeddings=self.image_embeddings,

@@ -1,6 +1,6 @@
 """ORACLE (test infrastructure): the I2VGen-XL denoising loop body of the reference pipeline restated on the oracle
 modules.  Follows /root/reference/i2vgen_xl/pipelines/i2vgen_xl_controlnet_adapter_pipeline.py:902-1118 (CFG on, no
-guess mode, dense frames) with diffusers v0.27.2 DDIMScheduler restated below.  The I2VGen-XL scheduler_config.json is
+guess mode, dense or sparse key frames) with diffusers v0.27.2 DDIMScheduler restated below.  The I2VGen-XL scheduler_config.json is
 not part of the reference repository; its values (squaredcos_cap_v2, rescale_betas_zero_snr, v_prediction,
 set_alpha_to_one, leading spacing, steps_offset 1) are restated from the published model card ("parity unpinned").
 Not imported by the product package."""
@@ -56,8 +56,11 @@ class DDIMScheduler:
 
 @torch.no_grad()
 def i2vgen_step(controlnet, adapter, unet, scheduler, i, latents, prompt_embeds, image_latents, image_embeddings, fps,
-                controlnet_prompt_embeds, images, router=None, masks=None, guidance_scale=9.0, cond_scale=1.0):
-    """latents (B,4,F,h,w).  One iteration of :902-1115."""
+                controlnet_prompt_embeds, images, router=None, masks=None, guidance_scale=9.0, cond_scale=1.0,
+                sparse_frames=None):
+    """latents (B,4,F,h,w).  One iteration of :902-1115.  sparse_frames: key-frame indices in [0, F) (:1024-1033,
+    :1053-1073); the reference supports one clip with its CFG pair (index s of the conditional half is s + F), restated
+    here for 2B clips as b*F + s."""
     t = scheduler.timesteps[i]
     b, c, f, h, w = latents.shape
     latent_model_input = scheduler.scale_model_input(torch.cat([latents] * 2), t)                  # :904-905
@@ -82,9 +85,26 @@ def i2vgen_step(controlnet, adapter, unet, scheduler, i, latents, prompt_embeds,
                     down_m[k] = down_m[k] + down[idx_e][k] * dw[k].repeat_interleave(f, dim=0)[e]
                     idx_e += 1
         down, mid = down_m, mid_m
+    n_adapter_frames = f
+    if sparse_frames is not None:                                                                   # :1026-1033
+        sparse_frames = [int(k) for k in sparse_frames]
+        rows = [bb * f + k for bb in range(2 * b) for k in sparse_frames]  # == sparse + [k + F ...] for one clip
+        down = [d[rows, :] for d in down]
+        mid = mid[rows, :]
+        n_adapter_frames = len(sparse_frames)
     a_down, a_mid = adapter(down_block_res_samples=[d.to(latents.dtype) for d in down],
-                            mid_block_res_sample=mid.to(latents.dtype), sparsity_masking=None, num_frames=f, timestep=t,
+                            mid_block_res_sample=mid.to(latents.dtype), sparsity_masking=sparse_frames,
+                            num_frames=n_adapter_frames, timestep=t,
                             encoder_hidden_states=image_embeddings[-1].unsqueeze(0))                # :1042-1049
+    if sparse_frames is not None:                                                                   # :1053-1073
+        # dense tensors are created by torch.zeros(...) -> float32 whatever the adapter dtype (reference quirk Q21)
+        def densify(x):
+            full = torch.zeros((2 * b * f, *x.shape[1:]), device=x.device)
+            for j, pos in enumerate(rows):
+                full[pos] = x[j]
+            return full
+        a_down = [densify(d) for d in a_down]
+        a_mid = densify(a_mid) if a_mid is not None else None
     # "(bs nf) c h w -> bs c nf h w" (the reference hard-codes bs=2; generalised to 2B clips)      # :1080-1083
     re5 = lambda x: x.reshape(2 * b, f, *x.shape[1:]).permute(0, 2, 1, 3, 4)  # noqa: E731
     a_mid5 = re5(a_mid) if a_mid is not None else None

@@ -261,7 +261,7 @@ def check_step_sdxl(steps=2):
     return _compare(f"SDXL denoise loop, {steps} steps, B=1 1024x1024", loop.latents, lat, None, tol_rel=2e-2, tol_max=8e-2)
 
 
-def check_step_i2vgen(steps=2, multi=False):
+def check_step_i2vgen(steps=2, multi=False, sparse=None):
     """Whole I2VGen-XL iterations (ControlNet[s] -> [router merge] -> adapter -> UNet -> CFG -> DDIM), B=1, F=4, 32^2."""
     from ctrl_adapter_b200.adapter import ControlNetAdapter, ControlNetRouter
     from ctrl_adapter_b200.controlnet import ControlNetModel, MultiControlNetModel
@@ -299,17 +299,17 @@ def check_step_i2vgen(steps=2, multi=False):
     sch = DDIMScheduler()
     sch.set_timesteps(50, device="cuda")
     loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, router, num_inference_steps=50, guidance_scale=9.0,
-                                         inference_expert_masks=masks)
+                                         inference_expert_masks=masks, sparse_frames=sparse)
     loop.prepare(control_images=images, **inp)
     lat = inp["latents"]
     with torch.no_grad():
         for i in range(steps):
             lat = i2vgen_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["image_latents"],
                               inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"], images,
-                              router=orouter, masks=masks)
+                              router=orouter, masks=masks, sparse_frames=sparse)
             loop.step(i)
     torch.cuda.synchronize()
-    return _compare(f"I2VGen-XL denoise loop multi={int(multi)}, {steps} steps, B=1 F=4 32x32", loop.latents_bcfhw(), lat,
+    return _compare(f"I2VGen-XL denoise loop multi={int(multi)} sparse={sparse}, {steps} steps, B=1 F=4 32x32", loop.latents_bcfhw(), lat,
                     None, tol_rel=2e-2, tol_max=8e-2)
 
 
@@ -319,6 +319,7 @@ GROUPS = {
     "unet": [lambda: check_unet_sdxl(2, 16, True), lambda: check_unet_sdxl(1, 32, False)],
     "video": [lambda: check_unet_i2vgen(1, 4, 32, True), lambda: check_unet_i2vgen(2, 2, 32, False)],
     "svd": [lambda: check_unet_svd(2, 4, 32, True), lambda: check_unet_svd(1, 3, 16, False)],
+    "sparse": [lambda: check_step_i2vgen(2, False, sparse=[0, 2])],
     "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
 }
 

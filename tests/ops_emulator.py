@@ -244,8 +244,66 @@ def i2vgen_latent_encoder(x, clips, frames, params):
     return out
 
 
+def router_weights(logits, mask):
+    lg = logits.float().clone()
+    if mask is not None:
+        lg[:, mask.to(torch.bool).logical_not()] = -1e6
+    return torch.softmax(lg, dim=-1)
+
+
+def router_merge(xs, w, ptr_table=None):
+    y = None
+    for x, wk in zip(xs, w.float()):
+        term = _r(x.float() * _r(wk))
+        y = term if y is None else _r(y + term)
+    return y.to(BF16)
+
+
+def cfg_euler(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None, model_in_next=None,
+              round_latents_bf16=True):
+    _, sigma, sigma_next, next_div = (float(v) for v in step_row)
+    u, c = eps_uncond.float(), eps_text.float()
+    eps = _r(u + _r(guidance * _r(c - u)))
+    x = latents.float()
+    x0 = x - _r(_r(torch.tensor(sigma)) * eps)
+    xn = x + (x - x0) / sigma * (sigma_next - sigma)
+    if round_latents_bf16:
+        xn = _r(xn)
+    if latents_out is None:
+        latents_out = torch.empty_like(latents)
+    latents_out.copy_(xn)
+    if model_in_next is not None:
+        model_in_next.copy_((xn / _r(torch.tensor(next_div))).to(BF16))
+    return latents_out
+
+
+def cfg_ddim(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None, model_in_next=None,
+             round_latents_bf16=True, v_prediction=False):
+    a_t, a_prev = float(step_row[1]), float(step_row[2])
+    sa, sb, sap, sbp = (torch.tensor(v).sqrt() for v in (a_t, 1.0 - a_t, a_prev, 1.0 - a_prev))
+    rr = _r if round_latents_bf16 else (lambda t: t)
+    sa, sb, sap, sbp = rr(sa), rr(sb), rr(sap), rr(sbp)
+    u, c = eps_uncond.float(), eps_text.float()
+    mo = _r(u + _r(guidance * _r(c - u)))
+    x = latents.float()
+    if v_prediction:
+        x0 = rr(rr(sa * x) - rr(sb * mo))
+        eps = rr(rr(sa * mo) + rr(sb * x))
+    else:
+        x0 = rr(rr(x - rr(sb * mo)) / sa)
+        eps = mo
+    xn = rr(rr(sap * x0) + rr(sbp * eps))
+    if latents_out is None:
+        latents_out = torch.empty_like(latents)
+    latents_out.copy_(xn)
+    if model_in_next is not None:
+        model_in_next.copy_(xn.to(BF16))
+    return latents_out
+
+
 _EMULATED = ["linear", "conv2d", "temporal_conv", "attention", "temporal_attention", "group_norm", "layer_norm",
-             "timestep_embedding", "silu", "add", "nchw_to_nhwc", "nhwc_to_nchw", "avgpool", "upsample2x", "i2vgen_latent_encoder"]
+             "timestep_embedding", "silu", "add", "nchw_to_nhwc", "nhwc_to_nchw", "avgpool", "upsample2x", "i2vgen_latent_encoder",
+             "router_weights", "router_merge", "cfg_euler", "cfg_ddim"]
 
 
 @contextlib.contextmanager

@@ -116,3 +116,47 @@ def test_emulated_unet_sdxl():
     from oracle.unet_sdxl import UNet2DConditionModel as O
     o, p = _pair(lambda: O(), lambda: UNet2DConditionModel(), 6)
     _compare(o, p, cases.unet_sdxl_inputs(2, 16, with_residuals=True))
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("sparse", [None, [0, 2]])
+def test_emulated_i2vgen_loop(sparse):
+    """Two whole I2VGen-XL iterations (ControlNet -> adapter -> UNet with injection -> CFG -> DDIM) through the emulated
+    op layer vs the restated reference loop, dense and with sparse key frames (gather -> adapter on 2 frames -> scatter
+    into zero residuals, i2vgen_xl pipeline :1024-1033, :1053-1073)."""
+    from ctrl_adapter_b200.adapter import ControlNetAdapter
+    from ctrl_adapter_b200.controlnet import ControlNetModel
+    from ctrl_adapter_b200.pipeline_i2vgen import I2VGenXLControlNetAdapterLoop
+    from ctrl_adapter_b200.unet_i2vgen import I2VGenXLUNet
+    from oracle.adapter import ControlNetAdapter as OA
+    from oracle.controlnet import ControlNetModel as OC
+    from oracle.pipeline_i2vgen import DDIMScheduler, i2vgen_step
+    from oracle.unet_i2vgen import I2VGenXLUNet as OU
+    from oracle.weights import seeded_tensor
+    b, f, r = 1, 4, 16
+    n = 2 * b * f
+    kw = dict(cases.ADAPTER_VIDEO_KW, num_frames=f)
+    oad, ad = _pair(lambda: OA(**kw), lambda: ControlNetAdapter(**kw), 2)
+    oun, un = _pair(lambda: OU(), lambda: I2VGenXLUNet(), 7)
+    ocn, cn = _pair(lambda: OC(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 4)
+    images = _q(torch.sigmoid(seeded_tensor("v_img", (n, 3, 8 * r, 8 * r))))
+    inp = dict(latents=seeded_tensor("v_lat", (b, 4, f, r, r)), prompt_embeds=seeded_tensor("v_pe", (2 * b, 77, 1024)),
+               image_latents=seeded_tensor("v_il", (2 * b, 4, f, r, r)),
+               image_embeddings=seeded_tensor("v_ie", (2 * b, 1, 1024)), fps=torch.tensor([16.0] * (2 * b)),
+               controlnet_prompt_embeds=seeded_tensor("v_cpe", (n, 77, 768)))
+    inp = {k: _q(v) for k, v in inp.items()}
+    sch = DDIMScheduler()
+    sch.set_timesteps(50)
+    lat = inp["latents"]
+    with emu.patched_ops():
+        loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, None, num_inference_steps=50, guidance_scale=9.0,
+                                             sparse_frames=sparse)
+        loop.prepare(control_images=images, **inp)
+        for i in range(2):
+            lat = i2vgen_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["image_latents"],
+                              inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"], images,
+                              sparse_frames=sparse)
+            loop.step(i)
+    ours = loop.latents_bcfhw().float()
+    rel = float((ours - lat).norm() / lat.norm())
+    assert rel <= 2e-2, rel
