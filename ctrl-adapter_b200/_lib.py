@@ -84,6 +84,7 @@ SIGNATURES = {
     "ca_router_weights": [_P, _P, _I, _I, _P, _P],
     "ca_router_merge": [_P, _P, _I, _L, _P, _P],
     "ca_cfg_euler": [_P, _P, _P, _L, _F, _P, _I, _P, _P, _P],
+    "ca_cfg_euler_v": [_P, _P, _P, _L, _P, _I, _L, _P, _I, _P, _P, _P],
     "ca_cfg_ddim": [_P, _P, _P, _L, _F, _P, _I, _I, _P, _P, _P],
     "ca_i2vgen_latent_encoder": [_P, _I, _I, _L, _I, _P, _P, _P],
     "ca_temporal_attention": [_P, _P, _P, _I, _I, _L, _I, _F, _L, _P, _P],

@@ -311,6 +311,13 @@ int ca_cfg_euler(const void* eu, const void* et, const float* lat, int64_t n, fl
   CA_LAUNCH(ca::launch_cfg_euler((const __nv_bfloat16*)eu, (const __nv_bfloat16*)et, lat, n, g, step_row,
                                  round_latents_bf16, lat_out, (__nv_bfloat16*)next_in, (cudaStream_t)s), "cfg_euler");
 }
+int ca_cfg_euler_v(const void* eu, const void* et, const float* lat, int64_t n, const float* guidance, int32_t frames,
+                   int64_t frame_elems, const float* step_row, int32_t round_latents_bf16, float* lat_out, void* next_in,
+                   void* s) {
+  CA_LAUNCH(ca::launch_cfg_euler_v((const __nv_bfloat16*)eu, (const __nv_bfloat16*)et, lat, n, guidance, frames,
+                                   frame_elems, step_row, round_latents_bf16, lat_out, (__nv_bfloat16*)next_in,
+                                   (cudaStream_t)s), "cfg_euler_v");
+}
 int ca_cfg_ddim(const void* eu, const void* et, const float* lat, int64_t n, float g, const float* step_row,
                 int32_t round_latents_bf16, int32_t v_prediction, float* lat_out, void* next_in, void* s) {
   CA_LAUNCH(ca::launch_cfg_ddim((const __nv_bfloat16*)eu, (const __nv_bfloat16*)et, lat, n, g, step_row,

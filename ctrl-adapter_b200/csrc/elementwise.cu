@@ -294,6 +294,43 @@ cudaError_t launch_cfg_euler(const __nv_bfloat16* eps_uncond, const __nv_bfloat1
                                                            round_latents_bf16, latents_out, model_in_next);
   return cudaGetLastError();
 }
+// Euler, v-prediction, per-frame guidance (SVD loop, svd/pipelines/svd_controlnet_adapter_pipeline.py:781-787 with the
+// diffusers v0.27.2 EulerDiscreteScheduler.step): row = {t, sigma, sigma_next, sqrt(sigma_next^2+1)};
+// guidance[f] (bf16-valued) for frame f = (i / frame_elems) % frames of a [clips, frames, C, H, W] latent.
+//   mo   = u + g_f (c - u)                                  (bf16 ops)
+//   x0   = mo * bf16(-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1)   (bf16 product, then fp32: the scheduler up-casts x)
+//   x'   = x + (x - x0) / sigma * (sigma_next - sigma)      -> rounded to the model dtype
+__global__ void cfg_euler_v_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
+                                   const float* __restrict__ lat, long long n, const float* __restrict__ guidance,
+                                   int frames, long long frame_elems, const float* __restrict__ row, int round_lat,
+                                   float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
+  const float sigma = row[1], sigma_next = row[2], next_div = round_bf16(row[3]);
+  const float c_out = round_bf16(-sigma / sqrtf(sigma * sigma + 1.0f));
+  const float c_skip_den = sigma * sigma + 1.0f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float g = guidance[(i / frame_elems) % frames];
+    const float u = __bfloat162float(eu[i]), c = __bfloat162float(et[i]);
+    const float mo = round_bf16(u + round_bf16(g * round_bf16(c - u)));
+    const float x = lat[i];
+    const float x0 = round_bf16(mo * c_out) + x / c_skip_den;
+    const float d = (x - x0) / sigma;
+    float xn = x + d * (sigma_next - sigma);
+    if (round_lat) xn = round_bf16(xn);
+    lat_out[i] = xn;
+    if (next_in) next_in[i] = __float2bfloat16_rn(xn / next_div);
+  }
+}
+cudaError_t launch_cfg_euler_v(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
+                               long long n, const float* guidance, int frames, long long frame_elems,
+                               const float* step_row, int round_latents_bf16, float* latents_out,
+                               __nv_bfloat16* model_in_next, cudaStream_t stream) {
+  if (frames < 1 || frame_elems < 1 || n % (static_cast<long long>(frames) * frame_elems) != 0) return cudaErrorInvalidValue;
+  cfg_euler_v_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, frames,
+                                                             frame_elems, step_row, round_latents_bf16, latents_out,
+                                                             model_in_next);
+  return cudaGetLastError();
+}
 // DDIM (eta 0): row = {t, alpha_prod_t, alpha_prod_prev, -}; epsilon- or v-prediction model output
 __global__ void cfg_ddim_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
                                 const float* __restrict__ lat, long long n, float g, const float* __restrict__ row,

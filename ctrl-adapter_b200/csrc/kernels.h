@@ -83,6 +83,10 @@ cudaError_t launch_router_weights(const float* logits, const unsigned char* mask
                                   float* weights, cudaStream_t stream);
 cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, int nactive, long long n,
                                 __nv_bfloat16* y, cudaStream_t stream);
+cudaError_t launch_cfg_euler_v(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
+                               long long n, const float* guidance, int frames, long long frame_elems,
+                               const float* step_row, int round_latents_bf16, float* latents_out,
+                               __nv_bfloat16* model_in_next, cudaStream_t stream);
 cudaError_t launch_cfg_euler(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
                              long long n, float guidance, const float* step_row, int round_latents_bf16,
                              float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream);

@@ -544,6 +544,21 @@ def cfg_euler(eps_uncond, eps_text, latents, guidance, step_row, latents_out=Non
     return latents_out
 
 
+def cfg_euler_v(eps_uncond, eps_text, latents, guidance_per_frame, frames: int, step_row, latents_out=None,
+                model_in_next=None, round_latents_bf16: bool = True):
+    """SVD loop update: latents fp32 [clips, frames, C, H, W]; guidance_per_frame device fp32 [frames];
+    step_row: device fp32 [4] = (t, sigma, sigma_next, sqrt(sigma_next^2+1))."""
+    _req(eps_uncond); _req(eps_text); _req(latents, torch.float32); _req(step_row, torch.float32)
+    _req(guidance_per_frame, torch.float32)
+    if latents_out is None:
+        latents_out = torch.empty_like(latents)
+    frame_elems = latents.numel() // (latents.shape[0] * frames)
+    _launch("cfg_euler", 0.0, 0.0, "ca_cfg_euler_v", eps_uncond.data_ptr(), eps_text.data_ptr(), latents.data_ptr(),
+            latents.numel(), guidance_per_frame.data_ptr(), int(frames), int(frame_elems), step_row.data_ptr(),
+            int(round_latents_bf16), latents_out.data_ptr(), _ptr(model_in_next), _stream())
+    return latents_out
+
+
 def cfg_ddim(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None, model_in_next=None,
              round_latents_bf16: bool = True, v_prediction: bool = False):
     """step_row: device fp32 [4] = (t, alpha_prod_t, alpha_prod_prev, -)."""

@@ -96,3 +96,31 @@ class DDIMSchedule:
             prev = t - self.step_ratio
             rows[i] = (t, self.ac[t], self.ac[prev] if prev >= 0 else self.final_alpha, 0.0)
         return rows
+
+
+class EulerKarrasVSchedule:
+    """EulerDiscreteScheduler as configured for Stable Video Diffusion (stabilityai/stable-video-diffusion-img2vid
+    scheduler_config.json, restated from memory -- the file is not part of the reference repo): v_prediction,
+    timestep_type "continuous" (t = 0.25 ln sigma), Karras sigmas (rho 7) between sigma_max 700 and sigma_min 0.002,
+    "leading" spacing (init_noise_sigma = sqrt(sigma_max^2 + 1)).  Used by pipeline_svd (svd pipeline :600-602, :775)."""
+
+    def __init__(self, num_inference_steps: int, sigma_min: float = 0.002, sigma_max: float = 700.0, rho: float = 7.0):
+        ramp = np.linspace(0, 1, num_inference_steps)
+        lo, hi = sigma_min ** (1 / rho), sigma_max ** (1 / rho)
+        sig = ((hi + ramp * (lo - hi)) ** rho).astype(np.float32)
+        self.timesteps = (0.25 * np.log(sig)).astype(np.float32)       # fed to the UNet
+        self.sigmas = np.concatenate([sig, [0.0]]).astype(np.float32)
+        self.init_noise_sigma = float((self.sigmas.max() ** 2 + 1) ** 0.5)
+        interval = 1000 // num_inference_steps
+        # the ControlNet / adapter timestep is derived from the step index (svd pipeline :676-681)
+        self.control_timesteps = np.array([1000 - (i + 1) * interval + 1 for i in range(num_inference_steps)],
+                                          dtype=np.float32)
+
+    def table(self):
+        """[steps, 4] fp32 rows (t, sigma, sigma_next, sqrt(sigma_next^2 + 1)) consumed by ca_cfg_euler_v."""
+        n = len(self.timesteps)
+        rows = np.zeros((n, 4), dtype=np.float32)
+        for i in range(n):
+            rows[i] = (self.timesteps[i], self.sigmas[i], self.sigmas[i + 1],
+                       np.sqrt(np.float32(self.sigmas[i + 1]) ** 2 + np.float32(1.0)))
+        return rows

@@ -179,6 +179,13 @@ int ca_router_merge(const void* const* xs, const float* w, int32_t nactive, int6
 int ca_cfg_euler(const void* eps_uncond, const void* eps_text, const float* latents_in, int64_t n, float guidance,
                  const float* step_row, int32_t round_latents_bf16, float* latents_out, void* model_in_next,
                  void* cuda_stream);
+/* Euler, v-prediction, per-frame guidance = the SVD loop (svd pipeline :781-787; EulerDiscreteScheduler with
+ * prediction_type v_prediction): latents [clips, frames, C, H, W], guidance: DEVICE fp32 [frames] (bf16-valued, the
+ * pipeline's linspace(min, max, F) in the latent dtype), frame_elems = C*H*W.  step_row as for ca_cfg_euler.
+ *   mo = u + g_f (c - u);  x0 = mo * (-sigma / sqrt(sigma^2+1)) + x / (sigma^2+1);  x' = x + (x - x0)/sigma * (sigma_next - sigma) */
+int ca_cfg_euler_v(const void* eps_uncond, const void* eps_text, const float* latents_in, int64_t n,
+                   const float* guidance, int32_t frames, int64_t frame_elems, const float* step_row,
+                   int32_t round_latents_bf16, float* latents_out, void* model_in_next, void* cuda_stream);
 int ca_cfg_ddim(const void* eps_uncond, const void* eps_text, const float* latents_in, int64_t n, float guidance,
                 const float* step_row, int32_t round_latents_bf16, int32_t v_prediction, float* latents_out,
                 void* model_in_next, void* cuda_stream);

@@ -313,6 +313,69 @@ def check_step_i2vgen(steps=2, multi=False, sparse=None):
                     None, tol_rel=2e-2, tol_max=8e-2)
 
 
+def check_cfg_euler_v():
+    """ca_cfg_euler_v against the same arithmetic in PyTorch (bf16 rounding points of the reference's tensor ops)."""
+    from ctrl_adapter_b200 import ops
+    from tests import ops_emulator as emu
+    g = torch.Generator(device="cpu").manual_seed(5)
+    b, f, c, h, w = 2, 5, 4, 16, 24
+    eu = torch.randn(b, f, c, h, w, generator=g).to(BF16).cuda()
+    et = torch.randn(b, f, c, h, w, generator=g).to(BF16).cuda()
+    lat = (torch.randn(b, f, c, h, w, generator=g) * 30).to(BF16).float().cuda()
+    guid = torch.linspace(1.0, 3.0, f).to(BF16).float().cuda()
+    row = torch.tensor([1.2, 12.5, 7.25, (7.25 ** 2 + 1) ** 0.5], dtype=torch.float32).cuda()
+    nxt = torch.empty_like(eu)
+    out = ops.cfg_euler_v(eu, et, lat, guid, f, row, model_in_next=nxt)
+    torch.cuda.synchronize()
+    nxt_ref = torch.empty_like(eu)
+    ref = emu.cfg_euler_v(eu, et, lat, guid, f, row.cpu(), model_in_next=nxt_ref)
+    r1 = _compare("cfg_euler_v latents", out, ref, None, tol_rel=2e-3, tol_max=1e-2)
+    r2 = _compare("cfg_euler_v next model input", nxt, nxt_ref, None, tol_rel=2e-3, tol_max=1e-2)
+    return r1, r2
+
+
+def check_step_svd(steps=2, sparse=None):
+    """Whole SVD iterations (ControlNet -> adapter -> SVD UNet -> per-frame CFG -> Euler v-prediction), B=1, F=4, 32^2."""
+    from ctrl_adapter_b200.adapter import ControlNetAdapter
+    from ctrl_adapter_b200.controlnet import ControlNetModel
+    from ctrl_adapter_b200.pipeline_svd import SVDControlNetAdapterLoop
+    from ctrl_adapter_b200.unet_svd import UNetSpatioTemporalConditionModel
+    from oracle import cases
+    from oracle.adapter import ControlNetAdapter as OA
+    from oracle.controlnet import ControlNetModel as OC
+    from oracle.pipeline_svd import EulerDiscreteSchedulerSVD, svd_step
+    from oracle.unet_svd import UNetSpatioTemporalConditionModel as OU
+    from oracle.weights import seeded_tensor
+    b, f, r, nsteps = 1, 4, 32, 25
+    n = 2 * b * f
+    kw = dict(cases.ADAPTER_VIDEO_KW, backbone_model_name="svd", num_frames=f)
+    oad, ad = _build_pair(lambda: OA(**kw), lambda: ControlNetAdapter(**kw), 2)
+    oun, un = _build_pair(lambda: OU(**cases.UNET_SVD_KW), lambda: UNetSpatioTemporalConditionModel(**cases.UNET_SVD_KW), 8)
+    ocn, cn = _build_pair(lambda: OC(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 4)
+    images = _q(torch.sigmoid(seeded_tensor("s_img", (n, 3, 8 * r, 8 * r)))).cuda()
+    il = seeded_tensor("s_il", (b, f, 4, r, r))
+    inp = dict(latents=seeded_tensor("s_lat", (b, f, 4, r, r)), image_latents=torch.cat([torch.zeros_like(il), il]),
+               image_embeddings=torch.cat([torch.zeros(b, 1, 1024), seeded_tensor("s_ie", (b, 1, 1024))]),
+               added_time_ids=torch.tensor([[6.0, 127.0, 0.02]] * (2 * b)),
+               controlnet_prompt_embeds=seeded_tensor("s_cpe", (n, 77, 768)))
+    inp = {k: _q(v).cuda() for k, v in inp.items()}
+    sch = EulerDiscreteSchedulerSVD()
+    sch.set_timesteps(nsteps, device="cuda")
+    flags = dict(use_size_512=False, skip_conv_in=True, skip_time_emb=False)
+    loop = SVDControlNetAdapterLoop(cn, ad, un, num_inference_steps=nsteps, sparse_frames=sparse, **flags)
+    loop.prepare(control_images=images, **inp)
+    lat = (inp["latents"] * sch.init_noise_sigma).to(BF16)
+    with torch.no_grad():
+        for i in range(steps):
+            lat = svd_step(ocn, oad, oun, sch, i, lat.float(), inp["image_latents"], inp["image_embeddings"],
+                           inp["added_time_ids"], inp["controlnet_prompt_embeds"], images, sparse_frames=sparse,
+                           **flags).to(BF16)
+            loop.step(i)
+    torch.cuda.synchronize()
+    return _compare(f"SVD denoise loop sparse={sparse}, {steps} steps, B=1 F=4 32x32", loop.latents, lat.float(), None,
+                    tol_rel=2e-2, tol_max=8e-2)
+
+
 GROUPS = {
     "adapter": [lambda: check_adapter("sdxl", 2, 8), lambda: check_adapter("video", 1, 8, 4), check_router],
     "controlnet": [lambda: check_controlnet(2, 8), lambda: check_controlnet(2, 16, True, 0.75)],
@@ -320,6 +383,7 @@ GROUPS = {
     "video": [lambda: check_unet_i2vgen(1, 4, 32, True), lambda: check_unet_i2vgen(2, 2, 32, False)],
     "svd": [lambda: check_unet_svd(2, 4, 32, True), lambda: check_unet_svd(1, 3, 16, False)],
     "sparse": [lambda: check_step_i2vgen(2, False, sparse=[0, 2])],
+    "svd_loop": [check_cfg_euler_v, check_step_svd, lambda: check_step_svd(2, sparse=[1, 3])],
     "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
 }
 

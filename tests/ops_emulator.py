@@ -277,6 +277,26 @@ def cfg_euler(eps_uncond, eps_text, latents, guidance, step_row, latents_out=Non
     return latents_out
 
 
+def cfg_euler_v(eps_uncond, eps_text, latents, guidance_per_frame, frames, step_row, latents_out=None,
+                model_in_next=None, round_latents_bf16=True):
+    _, sigma, sigma_next, next_div = (float(v) for v in step_row)
+    g = guidance_per_frame.float().reshape(1, frames, *([1] * (latents.dim() - 2)))
+    u, c = eps_uncond.float(), eps_text.float()
+    mo = _r(u + _r(g * _r(c - u)))
+    x = latents.float()
+    c_out = _r(torch.tensor(-sigma / math.sqrt(sigma * sigma + 1.0)))
+    x0 = _r(mo * c_out) + x / (sigma * sigma + 1.0)
+    xn = x + (x - x0) / sigma * (sigma_next - sigma)
+    if round_latents_bf16:
+        xn = _r(xn)
+    if latents_out is None:
+        latents_out = torch.empty_like(latents)
+    latents_out.copy_(xn)
+    if model_in_next is not None:
+        model_in_next.copy_((xn / _r(torch.tensor(next_div))).to(BF16))
+    return latents_out
+
+
 def cfg_ddim(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None, model_in_next=None,
              round_latents_bf16=True, v_prediction=False):
     a_t, a_prev = float(step_row[1]), float(step_row[2])
@@ -303,7 +323,7 @@ def cfg_ddim(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None
 
 _EMULATED = ["linear", "conv2d", "temporal_conv", "attention", "temporal_attention", "group_norm", "layer_norm",
              "timestep_embedding", "silu", "add", "nchw_to_nhwc", "nhwc_to_nchw", "avgpool", "upsample2x", "i2vgen_latent_encoder",
-             "router_weights", "router_merge", "cfg_euler", "cfg_ddim"]
+             "router_weights", "router_merge", "cfg_euler", "cfg_euler_v", "cfg_ddim"]
 
 
 @contextlib.contextmanager

@@ -160,3 +160,50 @@ def test_emulated_i2vgen_loop(sparse):
     ours = loop.latents_bcfhw().float()
     rel = float((ours - lat).norm() / lat.norm())
     assert rel <= 2e-2, rel
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("sparse", [None, [0, 2]])
+def test_emulated_svd_loop(sparse):
+    """Two whole SVD iterations (ControlNet -> adapter -> SVD UNet with 5-D-equivalent injection -> per-frame CFG ->
+    Euler v-prediction) through the emulated op layer vs the restated reference loop (oracle/pipeline_svd.py)."""
+    from ctrl_adapter_b200.adapter import ControlNetAdapter
+    from ctrl_adapter_b200.controlnet import ControlNetModel
+    from ctrl_adapter_b200.pipeline_svd import SVDControlNetAdapterLoop
+    from ctrl_adapter_b200.unet_svd import UNetSpatioTemporalConditionModel
+    from oracle.adapter import ControlNetAdapter as OA
+    from oracle.controlnet import ControlNetModel as OC
+    from oracle.pipeline_svd import EulerDiscreteSchedulerSVD, svd_step
+    from oracle.unet_svd import UNetSpatioTemporalConditionModel as OU
+    from oracle.weights import seeded_tensor
+    b, f, r, steps = 1, 3, 16, 25
+    n = 2 * b * f
+    kw = dict(cases.ADAPTER_VIDEO_KW, backbone_model_name="svd", num_frames=f)
+    oad, ad = _pair(lambda: OA(**kw), lambda: ControlNetAdapter(**kw), 2)
+    oun, un = _pair(lambda: OU(**cases.UNET_SVD_KW), lambda: UNetSpatioTemporalConditionModel(**cases.UNET_SVD_KW), 8)
+    ocn, cn = _pair(lambda: OC(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 4)
+    images = _q(torch.sigmoid(seeded_tensor("s_img", (n, 3, 8 * r, 8 * r))))
+    il = seeded_tensor("s_il", (b, f, 4, r, r))
+    inp = dict(latents=seeded_tensor("s_lat", (b, f, 4, r, r)),
+               image_latents=torch.cat([torch.zeros_like(il), il]),
+               image_embeddings=torch.cat([torch.zeros(b, 1, 1024), seeded_tensor("s_ie", (b, 1, 1024))]),
+               added_time_ids=torch.tensor([[6.0, 127.0, 0.02]] * (2 * b)),
+               controlnet_prompt_embeds=seeded_tensor("s_cpe", (n, 77, 768)))
+    inp = {k: _q(v) for k, v in inp.items()}
+    sch = EulerDiscreteSchedulerSVD()
+    sch.set_timesteps(steps)
+    lat = (inp["latents"] * sch.init_noise_sigma).to(BF16)  # prepare_latents: the latent dtype is the model dtype
+    flags = dict(use_size_512=False, skip_conv_in=True, skip_time_emb=False)
+    with emu.patched_ops():
+        loop = SVDControlNetAdapterLoop(cn, ad, un, num_inference_steps=steps, sparse_frames=sparse, **flags)
+        loop.prepare(control_images=images, **inp)
+        assert float((loop.latents - lat.float()).abs().max()) == 0.0
+        for i in range(2):
+            # oracle in fp32 modules but bf16 latents / model outputs, as the reference runs them under autocast
+            lat = svd_step(ocn, oad, oun, sch, i, lat.float(), inp["image_latents"], inp["image_embeddings"],
+                           inp["added_time_ids"], inp["controlnet_prompt_embeds"], images, sparse_frames=sparse,
+                           **flags).to(BF16)
+            loop.step(i)
+    ours = loop.latents
+    rel = float((ours - lat.float()).norm() / lat.float().norm())
+    assert rel <= 2e-2, rel

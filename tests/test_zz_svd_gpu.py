@@ -1,5 +1,6 @@
 """pytest -m gpu: checks of code written after the round's GPU budget was spent -- the Stable-Video-Diffusion UNet
-(ctrl_adapter_b200.unet_svd) and the sparse key-frame path of the I2VGen-XL loop -- against the oracle.
+(ctrl_adapter_b200.unet_svd), the SVD denoising loop with its new ca_cfg_euler_v kernel (ctrl_adapter_b200.pipeline_svd)
+and the sparse key-frame path of the I2VGen-XL loop -- against the oracle.
 
 The module is composed from building blocks that are GPU-validated through the adapter / I2VGen paths, and the oracle it
 is compared with is bit-exact against the reference class on CPU (tests/test_oracle_golden.py), but this composition had
@@ -18,7 +19,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("group", ["svd", "sparse"])
+@pytest.mark.parametrize("group", ["svd", "sparse", "svd_loop"])
 def test_pending_first_hardware_run(group):
     if not torch.cuda.is_available():
         pytest.fail("GPU tests selected but no CUDA device is visible (there is no CPU fallback to test)")
