@@ -43,8 +43,9 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--batch", type=int, default=8, help="images per GPU (BASELINE config: 8)")
     p.add_argument("--res", type=int, default=1024)
-    p.add_argument("--workload", default="sdxl", choices=["sdxl", "i2vgen"],
-                   help="sdxl = BASELINE.json configs[1] (headline); i2vgen = configs[2] (I2VGen-XL 16f 512x512, batch 4)")
+    p.add_argument("--workload", default="sdxl", choices=["sdxl", "i2vgen", "svd"],
+                   help="sdxl = BASELINE.json configs[1] (headline); i2vgen = configs[2] (I2VGen-XL 16f 512x512, batch 4); "
+                        "svd = configs[3] (SVD 14f 576x1024, batch 2 per GPU)")
     p.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     p.add_argument("--skip-cpu-baseline", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -286,6 +287,34 @@ def main():
         wl_name = (f"SDXL+depth ControlNet+Ctrl-Adapter {a.res}x{a.res}, batch {a.batch} per GPU "
                    f"(CFG: {n_samples} frame-samples), one pipeline-loop iteration per step")
         base_cfg = "BASELINE.json configs[1]"
+    elif a.workload == "svd":
+        from ctrl_adapter_b200.pipeline_svd import SVDControlNetAdapterLoop
+        from ctrl_adapter_b200.unet_svd import UNetSpatioTemporalConditionModel
+        frames, vb = 14, (a.batch if a.batch != 8 else 2)
+        lh, lw = 72, 128  # 576 x 1024 video -> 72 x 128 latents; needs use_size_512=False (cfg 4)
+        with torch.device(dev):
+            ad = ControlNetAdapter("svd", num_blocks=1, num_frames=frames, cross_attention_dim=1024,
+                                   add_spatial_resnet=True, add_temporal_resnet=True, add_spatial_transformer=True,
+                                   add_temporal_transformer=True, add_adapter_location_A=True,
+                                   add_adapter_location_B=True, add_adapter_location_C=True,
+                                   add_adapter_location_D=True, add_adapter_location_M=True)
+            un = UNetSpatioTemporalConditionModel(num_attention_heads=(5, 10, 20, 20), num_frames=frames)
+        cn, ad, un = (m.to(BF16).eval() for m in (cn, ad, un))
+        loop = SVDControlNetAdapterLoop(cn, ad, un, num_inference_steps=25, min_guidance_scale=1.0, max_guidance_scale=3.0,
+                                        use_size_512=False, skip_conv_in=True)
+        g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+        r = lambda *s_: torch.randn(*s_, generator=g).to(dev)  # noqa: E731
+        n_samples = 2 * vb * frames
+        il = r(vb, frames, 4, lh, lw)
+        loop.prepare(latents=r(vb, frames, 4, lh, lw), image_latents=torch.cat([torch.zeros_like(il), il]),
+                     image_embeddings=torch.cat([torch.zeros(vb, 1, 1024, device=dev), r(vb, 1, 1024)]),
+                     added_time_ids=torch.tensor([[13.0, 127.0, 0.02]] * (2 * vb), device=dev),
+                     controlnet_prompt_embeds=r(n_samples, 77, 768),
+                     control_images=torch.rand(n_samples, 3, 8 * lh, 8 * lw, generator=g).to(dev))
+        tflop_per_sample = 0.7735 + 1.679 + 3.192  # ControlNet, video adapter, SVD UNet @72x128 (rough)
+        wl_name = (f"SVD+depth ControlNet+Ctrl-Adapter 14 frames 576x1024, batch {vb} per GPU "
+                   f"(CFG: {n_samples} frame-samples), one pipeline-loop iteration per step")
+        base_cfg = "BASELINE.json configs[3]"
     else:
         from ctrl_adapter_b200.pipeline_i2vgen import I2VGenXLControlNetAdapterLoop
         from ctrl_adapter_b200.unet_i2vgen import I2VGenXLUNet
@@ -312,6 +341,7 @@ def main():
         base_cfg = "BASELINE.json configs[2]"
 
     use_graph = not a.no_graph
+    nsteps = loop.num_inference_steps  # the schedule wraps around when more steps are timed than it has
     l0 = ops.PROFILER.launches
     loop.step(0)  # packs weights, sets kernel attributes
     launches_per_step = ops.PROFILER.launches - l0
@@ -320,7 +350,7 @@ def main():
         loop.capture(warmup=1)
     stepfn = loop.step_graph if use_graph else loop.step
     for i in range(a.warmup):
-        stepfn(i % 50)
+        stepfn(i % nsteps)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -330,7 +360,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(a.steps):
-        stepfn((a.warmup + i) % 50)
+        stepfn((a.warmup + i) % nsteps)
     if dist:  # the single collective of the job: gather every rank's final latents (C1 in SURVEY.md)
         from ctrl_adapter_b200.distributed import gather_latents
         gathered = gather_latents(loop.latents, loop.latents.shape[0] * world)
@@ -365,7 +395,7 @@ def main():
         for i in range(ke):
             loop.latents.copy_(host_lat, non_blocking=True)       # H2D: this step's latents
             loop.model_in.copy_(host_in, non_blocking=True)       # H2D: scaled model input
-            loop.step(i % 50)                                     # ControlNet / adapter / UNet module forward()s
+            loop.step(i % nsteps)                                 # ControlNet / adapter / UNet module forward()s
             host_lat.copy_(loop.latents, non_blocking=True)       # D2H: the step's result
             host_in.copy_(loop.model_in, non_blocking=True)
             torch.cuda.current_stream().synchronize()             # the host consumes the result every step
@@ -483,8 +513,10 @@ def main():
     if rank == 0:
         step_tflop = n_samples * tflop_per_sample
         line = {
-            "metric": "denoising steps/sec (SDXL 1024x1024 + depth ControlNet + Ctrl-Adapter, batch 8)" if a.workload == "sdxl"
-            else "denoising steps/sec (I2VGen-XL 16f 512x512 + depth ControlNet + Ctrl-Adapter, batch 4)",
+            "metric": {"sdxl": "denoising steps/sec (SDXL 1024x1024 + depth ControlNet + Ctrl-Adapter, batch 8)",
+                       "i2vgen": "denoising steps/sec (I2VGen-XL 16f 512x512 + depth ControlNet + Ctrl-Adapter, batch 4)",
+                       "svd": "denoising steps/sec (SVD 14f 576x1024 + depth ControlNet + Ctrl-Adapter, batch 2 per GPU)"}[
+                           a.workload],
             "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
