@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kAttnThreads, (DQ == 1) ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   using Cfg = AttnCfg<DQ>;
+  CA_PDL_TRIGGER();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -159,6 +160,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
+  CA_PDL_WAIT();  // prologue (barriers, TMEM) done: from here on global memory of the previous kernel is consumed
   [[maybe_unused]] const uint32_t tmem_p = tmem_base + 192;  // PT: bf16 P, two keys per 32-bit cell, 64 columns
 
   if (warp < 4) {
@@ -514,7 +516,8 @@ static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const C
   // developer knobs: CA_ATTN_GRID=items launches one CTA per work item (hardware block scheduler, dynamic balance)
   static const bool per_item = getenv("CA_ATTN_GRID") && getenv("CA_ATTN_GRID")[0] == 'i';
   const int grid = static_cast<int>((items < resident || per_item) ? items : resident);
-  attention_kernel<DQ, POLY, PT><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(q, k, v, p);
+  auto kern = attention_kernel<DQ, POLY, PT>;
+  CA_KERNEL_LAUNCH(kern, grid, kAttnThreads, Cfg::kSmemBytes, stream, q, k, v, p);
   return cudaGetLastError();
 }
 

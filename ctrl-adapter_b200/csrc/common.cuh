@@ -341,6 +341,42 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
 
 }  // namespace ca
 
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (experiment, compiled in with -DCA_PDL only; see scripts/build_variants.py).
+// With ~1500 launches per step, every kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) and the
+// launch latency itself sit between the tail of one kernel and the first useful cycle of the next.  Under CA_PDL each
+// kernel (a) tells the scheduler right away that its dependents may be launched as SMs free up and (b) waits for the
+// previous grid's completion only after its own prologue, before the first global-memory access.  Without the launch
+// attribute both instructions are no-ops, and without -DCA_PDL neither is emitted.
+// ---------------------------------------------------------------------------------------------------------------
+#ifdef CA_PDL
+#define CA_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;")
+#define CA_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+namespace ca {
+template <typename K, typename... A>
+inline cudaError_t launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+}  // namespace ca
+// `kernel` must be a plain identifier or a function pointer variable (no template commas inside the macro argument)
+#define CA_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)ca::launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+#else
+#define CA_PDL_TRIGGER()
+#define CA_PDL_WAIT()
+#define CA_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
 // Developer instrumentation (scripts/gemm_trace.py): cycles each role of a kernel spends blocked, 16 counters per CTA
 // written through the `trace` pointer of the kernel's Params struct.  Compiled out unless -DCA_TRACE.
 #ifdef CA_TRACE

@@ -18,6 +18,8 @@ static inline unsigned blocks_for(long long n, int threads, long long cap = 148L
 // ---------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, int dim, int flip, float shift,
                                           int round_t, __nv_bfloat16* __restrict__ out) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   const int half = dim / 2;
   const long long total = static_cast<long long>(n) * half;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -37,7 +39,7 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int n, in
 cudaError_t launch_timestep_embedding(const float* t, int n, int dim, int flip_sin_to_cos, float freq_shift,
                                       int round_t_bf16, __nv_bfloat16* out, cudaStream_t stream) {
   const long long total = static_cast<long long>(n) * (dim / 2);
-  timestep_embedding_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(t, n, dim, flip_sin_to_cos, freq_shift,
+  CA_KERNEL_LAUNCH(timestep_embedding_kernel, blocks_for(total, 256), 256, 0, stream, t, n, dim, flip_sin_to_cos, freq_shift,
                                                                         round_t_bf16, out);
   return cudaGetLastError();
 }
@@ -46,6 +48,8 @@ cudaError_t launch_timestep_embedding(const float* t, int n, int dim, int flip_s
 // silu / add (bf16, 8 elements per thread; n must be a multiple of 8 -- all channel counts here are)
 // ---------------------------------------------------------------------------------------------
 __global__ void silu_kernel(const uint4* __restrict__ x, long long nvec, uint4* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 u = x[i];
@@ -58,12 +62,14 @@ __global__ void silu_kernel(const uint4* __restrict__ x, long long nvec, uint4* 
 }
 cudaError_t launch_silu(const __nv_bfloat16* x, long long n, __nv_bfloat16* y, cudaStream_t stream) {
   if (n & 7) return cudaErrorInvalidValue;
-  silu_kernel<<<blocks_for(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), n / 8,
+  CA_KERNEL_LAUNCH(silu_kernel, blocks_for(n / 8, 256), 256, 0, stream, reinterpret_cast<const uint4*>(x), n / 8,
                                                           reinterpret_cast<uint4*>(y));
   return cudaGetLastError();
 }
 __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, long long nvec,
                            uint4* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 ua = a[i], ub = b[i];
@@ -82,7 +88,7 @@ __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict_
 cudaError_t launch_add(const __nv_bfloat16* a, const __nv_bfloat16* b, long long n, __nv_bfloat16* y,
                        cudaStream_t stream) {
   if (n & 7) return cudaErrorInvalidValue;
-  add_kernel<<<blocks_for(n / 8, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(a),
+  CA_KERNEL_LAUNCH(add_kernel, blocks_for(n / 8, 256), 256, 0, stream, reinterpret_cast<const uint4*>(a),
                                                          reinterpret_cast<const uint4*>(b), n / 8,
                                                          reinterpret_cast<uint4*>(y));
   return cudaGetLastError();
@@ -94,6 +100,8 @@ cudaError_t launch_add(const __nv_bfloat16* a, const __nv_bfloat16* b, long long
 template <typename SrcT>
 __global__ void nchw_to_nhwc_kernel(const SrcT* __restrict__ x, int c, long long hw, int c_pad,
                                     __nv_bfloat16* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long p0 = static_cast<long long>(blockIdx.x) * 32;
@@ -115,13 +123,15 @@ __global__ void nchw_to_nhwc_kernel(const SrcT* __restrict__ x, int c, long long
 cudaError_t launch_nchw_to_nhwc(const void* x, int src_fp32, int n, int c, long long hw, int c_pad, __nv_bfloat16* y,
                                 cudaStream_t stream) {
   dim3 grid(static_cast<unsigned>((hw + 31) / 32), (c_pad + 31) / 32, n), block(32, 8);
-  if (src_fp32) nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(x), c, hw, c_pad, y);
-  else nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), c, hw, c_pad, y);
+  if (src_fp32) CA_KERNEL_LAUNCH(nchw_to_nhwc_kernel<float>, grid, block, 0, stream, static_cast<const float*>(x), c, hw, c_pad, y);
+  else CA_KERNEL_LAUNCH(nchw_to_nhwc_kernel<__nv_bfloat16>, grid, block, 0, stream, static_cast<const __nv_bfloat16*>(x), c, hw, c_pad, y);
   return cudaGetLastError();
 }
 template <typename DstT>
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int c, int c_stride, long long hw,
                                     DstT* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long p0 = static_cast<long long>(blockIdx.x) * 32;
@@ -143,8 +153,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int c, 
 cudaError_t launch_nhwc_to_nchw(const __nv_bfloat16* x, int n, int c, int c_stride, long long hw, void* y,
                                 int dst_fp32, cudaStream_t stream) {
   dim3 grid(static_cast<unsigned>((hw + 31) / 32), (c + 31) / 32, n), block(32, 8);
-  if (dst_fp32) nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>(x, c, c_stride, hw, static_cast<float*>(y));
-  else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(x, c, c_stride, hw, static_cast<__nv_bfloat16*>(y));
+  if (dst_fp32) CA_KERNEL_LAUNCH(nhwc_to_nchw_kernel<float>, grid, block, 0, stream, x, c, c_stride, hw, static_cast<float*>(y));
+  else CA_KERNEL_LAUNCH(nhwc_to_nchw_kernel<__nv_bfloat16>, grid, block, 0, stream, x, c, c_stride, hw, static_cast<__nv_bfloat16*>(y));
   return cudaGetLastError();
 }
 
@@ -153,6 +163,8 @@ cudaError_t launch_nhwc_to_nchw(const __nv_bfloat16* x, int n, int c, int c_stri
 // ---------------------------------------------------------------------------------------------
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, int h, int w, int c, int oh, int ow,
                                long long total, __nv_bfloat16* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   const int ry = h / oh, rx = w / ow;
   const float inv = 1.0f / static_cast<float>(ry * rx);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -173,12 +185,14 @@ cudaError_t launch_avgpool(const __nv_bfloat16* x, int n, int h, int w, int c, i
                            cudaStream_t stream) {
   if (h % oh != 0 || w % ow != 0) return cudaErrorInvalidValue;
   const long long total = static_cast<long long>(n) * oh * ow * c;
-  avgpool_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(x, h, w, c, oh, ow, total, y);
+  CA_KERNEL_LAUNCH(avgpool_kernel, blocks_for(total, 256), 256, 0, stream, x, h, w, c, oh, ow, total, y);
   return cudaGetLastError();
 }
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, int h, int w, int nvec, long long total,
                                   uint4* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int v = static_cast<int>(i % nvec);
@@ -196,7 +210,7 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* x, int n, int h, int w, int c
                               cudaStream_t stream) {
   if (c & 7) return cudaErrorInvalidValue;
   const long long total = static_cast<long long>(n) * h * w * (c / 8);
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), h, w, c / 8, total,
+  CA_KERNEL_LAUNCH(upsample2x_kernel, blocks_for(total, 256), 256, 0, stream, reinterpret_cast<const uint4*>(x), h, w, c / 8, total,
                                                                 reinterpret_cast<uint4*>(y));
   return cudaGetLastError();
 }
@@ -206,6 +220,8 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* x, int n, int h, int w, int c
 // ---------------------------------------------------------------------------------------------
 __global__ void router_weights_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ mask,
                                       int nrouters, int nexperts, float* __restrict__ weights) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= nrouters) return;
   const int lane = threadIdx.x & 31;
@@ -227,13 +243,15 @@ cudaError_t launch_router_weights(const float* logits, const unsigned char* mask
                                   float* weights, cudaStream_t stream) {
   if (nexperts > 32 || nexperts < 1) return cudaErrorInvalidValue;
   const int wpb = 4;
-  router_weights_kernel<<<(nrouters + wpb - 1) / wpb, wpb * 32, 0, stream>>>(logits, mask, nrouters, nexperts, weights);
+  CA_KERNEL_LAUNCH(router_weights_kernel, (nrouters + wpb - 1) / wpb, wpb * 32, 0, stream, logits, mask, nrouters, nexperts, weights);
   return cudaGetLastError();
 }
 
 // y = sum_e w[e] * x_e with the reference's bf16 rounding after each multiply and add
 __global__ void router_merge_kernel(const __nv_bfloat16* const* __restrict__ xs, const float* __restrict__ w,
                                     int nactive, long long nvec, uint4* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float acc[8];
@@ -256,7 +274,7 @@ __global__ void router_merge_kernel(const __nv_bfloat16* const* __restrict__ xs,
 cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, int nactive, long long n,
                                 __nv_bfloat16* y, cudaStream_t stream) {
   if (n & 7) return cudaErrorInvalidValue;
-  router_merge_kernel<<<blocks_for(n / 8, 256), 256, 0, stream>>>(xs, w, nactive, n / 8, reinterpret_cast<uint4*>(y));
+  CA_KERNEL_LAUNCH(router_merge_kernel, blocks_for(n / 8, 256), 256, 0, stream, xs, w, nactive, n / 8, reinterpret_cast<uint4*>(y));
   return cudaGetLastError();
 }
 
@@ -270,6 +288,8 @@ cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, 
 __global__ void cfg_euler_kernel(const __nv_bfloat16* __restrict__ eu, const __nv_bfloat16* __restrict__ et,
                                  const float* __restrict__ lat, long long n, float g, const float* __restrict__ row,
                                  int round_lat, float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   // A 0-dim fp32 tensor combined with a bf16 tensor is first cast to bf16 by PyTorch's type promotion, so the
   // reference multiplies eps by bf16(sigma) and divides the next model input by bf16(sqrt(sigma_next^2+1)).
   const float sigma = row[1], sigma_next = row[2], next_div = round_bf16(row[3]);
@@ -290,7 +310,7 @@ __global__ void cfg_euler_kernel(const __nv_bfloat16* __restrict__ eu, const __n
 cudaError_t launch_cfg_euler(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
                              long long n, float guidance, const float* step_row, int round_latents_bf16,
                              float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream) {
-  cfg_euler_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, step_row,
+  CA_KERNEL_LAUNCH(cfg_euler_kernel, blocks_for(n, 256), 256, 0, stream, eps_uncond, eps_text, latents_in, n, guidance, step_row,
                                                            round_latents_bf16, latents_out, model_in_next);
   return cudaGetLastError();
 }
@@ -304,6 +324,8 @@ __global__ void cfg_euler_v_kernel(const __nv_bfloat16* __restrict__ eu, const _
                                    const float* __restrict__ lat, long long n, const float* __restrict__ guidance,
                                    int frames, long long frame_elems, const float* __restrict__ row, int round_lat,
                                    float* __restrict__ lat_out, __nv_bfloat16* __restrict__ next_in) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   const float sigma = row[1], sigma_next = row[2], next_div = round_bf16(row[3]);
   const float c_out = round_bf16(-sigma / sqrtf(sigma * sigma + 1.0f));
   const float c_skip_den = sigma * sigma + 1.0f;
@@ -326,7 +348,7 @@ cudaError_t launch_cfg_euler_v(const __nv_bfloat16* eps_uncond, const __nv_bfloa
                                const float* step_row, int round_latents_bf16, float* latents_out,
                                __nv_bfloat16* model_in_next, cudaStream_t stream) {
   if (frames < 1 || frame_elems < 1 || n % (static_cast<long long>(frames) * frame_elems) != 0) return cudaErrorInvalidValue;
-  cfg_euler_v_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, frames,
+  CA_KERNEL_LAUNCH(cfg_euler_v_kernel, blocks_for(n, 256), 256, 0, stream, eps_uncond, eps_text, latents_in, n, guidance, frames,
                                                              frame_elems, step_row, round_latents_bf16, latents_out,
                                                              model_in_next);
   return cudaGetLastError();
@@ -336,6 +358,8 @@ __global__ void cfg_ddim_kernel(const __nv_bfloat16* __restrict__ eu, const __nv
                                 const float* __restrict__ lat, long long n, float g, const float* __restrict__ row,
                                 int round_lat, int vpred, float* __restrict__ lat_out,
                                 __nv_bfloat16* __restrict__ next_in) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   const float a_t = row[1], a_prev = row[2];
   float sa = sqrtf(a_t), sb = sqrtf(1.f - a_t), sap = sqrtf(a_prev), sbp = sqrtf(1.f - a_prev);
   if (round_lat) {
@@ -375,7 +399,7 @@ __global__ void cfg_ddim_kernel(const __nv_bfloat16* __restrict__ eu, const __nv
 cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
                             long long n, float guidance, const float* step_row, int round_latents_bf16,
                             int v_prediction, float* latents_out, __nv_bfloat16* model_in_next, cudaStream_t stream) {
-  cfg_ddim_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(eps_uncond, eps_text, latents_in, n, guidance, step_row,
+  CA_KERNEL_LAUNCH(cfg_ddim_kernel, blocks_for(n, 256), 256, 0, stream, eps_uncond, eps_text, latents_in, n, guidance, step_row,
                                                           round_latents_bf16, v_prediction, latents_out, model_in_next);
   return cudaGetLastError();
 }
@@ -388,6 +412,8 @@ cudaError_t launch_cfg_ddim(const __nv_bfloat16* eps_uncond, const __nv_bfloat16
 __global__ void i2vgen_latent_encoder_kernel(const __nv_bfloat16* __restrict__ x, int frames, long long hw,
                                              int c_stride, const float* __restrict__ prm, long long total,
                                              __nv_bfloat16* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   __shared__ float sp[288];
   for (int i = threadIdx.x; i < 288; i += blockDim.x) sp[i] = prm[i];
   __syncthreads();
@@ -460,7 +486,7 @@ cudaError_t launch_i2vgen_latent_encoder(const __nv_bfloat16* x, int clips, int 
                                          const float* params, __nv_bfloat16* y, cudaStream_t stream) {
   if (frames > 32 || frames < 1) return cudaErrorInvalidValue;
   const long long total = static_cast<long long>(clips) * hw;
-  i2vgen_latent_encoder_kernel<<<static_cast<unsigned>((total + 63) / 64), 64, 0, stream>>>(x, frames, hw, c_stride,
+  CA_KERNEL_LAUNCH(i2vgen_latent_encoder_kernel, static_cast<unsigned>((total + 63) / 64), 64, 0, stream, x, frames, hw, c_stride,
                                                                                           params, total, y);
   return cudaGetLastError();
 }
@@ -479,6 +505,8 @@ __global__ void __launch_bounds__(128)
 temporal_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
                           const __nv_bfloat16* __restrict__ v, int frames, long long hw, int heads, float scale,
                           long long in_stride, long long total_warps, __nv_bfloat16* __restrict__ out) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   constexpr int D = 64 / HALVES;        // head-dim elements owned by a lane
   constexpr int MAXF = 32 / HALVES;     // max frames
   const long long wid = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -583,10 +611,10 @@ cudaError_t launch_temporal_attention(const __nv_bfloat16* q, const __nv_bfloat1
   const int threads = 128;
   const long long blocks = (total_warps * 32 + threads - 1) / threads;
   if (frames <= 16)
-    temporal_attention_kernel<2><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(q, k, v, frames, hw, heads, scale,
+    CA_KERNEL_LAUNCH(temporal_attention_kernel<2>, static_cast<unsigned>(blocks), threads, 0, stream, q, k, v, frames, hw, heads, scale,
                                                                                        in_row_stride, total_warps, out);
   else
-    temporal_attention_kernel<1><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(q, k, v, frames, hw, heads, scale,
+    CA_KERNEL_LAUNCH(temporal_attention_kernel<1>, static_cast<unsigned>(blocks), threads, 0, stream, q, k, v, frames, hw, heads, scale,
                                                                                        in_row_stride, total_warps, out);
   return cudaGetLastError();
 }

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                  const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   using Cfg = GemmCfg<BN, NCTA>;
+  CA_PDL_TRIGGER();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -149,6 +150,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
   if (NCTA == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  CA_PDL_WAIT();  // prologue done: the previous kernel's output (A, residual, bias ...) may be read from here on
 
   // decode tile -> (n tile, this CTA's 4-D M tile origin)
   auto tile_coords = [&](int tile, int& tn, int (&org)[4]) {
@@ -634,13 +636,18 @@ static cudaError_t launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, cons
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = NCTA;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#ifdef CA_PDL
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = 2;
+#endif
   return cudaLaunchKernelEx(&cfg, kern, a0, a1, w, p);
 }
 

@@ -21,6 +21,8 @@ __device__ __forceinline__ uint4 ld_nc(const void* p) {
 __global__ void __launch_bounds__(512)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1,
                 long long rows, int groups, int rows_per_block, double* __restrict__ sums) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   __shared__ float s_acc[64][2];
   const int C = c0 + c1;
   const int nvec = C >> 3;
@@ -103,7 +105,7 @@ cudaError_t launch_gn_stats(const __nv_bfloat16* x0, int c0, const __nv_bfloat16
   if (rpb < min_rpb) rpb = min_rpb;
   if (rpb > max_rpb) rpb = max_rpb;
   const int slabs = static_cast<int>((rows + rpb - 1) / rpb);
-  gn_stats_kernel<<<dim3(slabs, n), threads, 0, stream>>>(x0, c0, x1, c1, rows, groups, static_cast<int>(rpb), sums);
+  CA_KERNEL_LAUNCH(gn_stats_kernel, dim3(slabs, n), threads, 0, stream, x0, c0, x1, c1, rows, groups, static_cast<int>(rpb), sums);
   return cudaGetLastError();
 }
 
@@ -120,6 +122,8 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
                 int w, int imgs_per_sample, int groups, float eps, const double* __restrict__ sums,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int pix_per_block,
                 __nv_bfloat16* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   __shared__ float s_mean[64], s_rstd[64];
   const int C = c0 + c1;
   const int nvec = C >> 3;
@@ -210,9 +214,12 @@ cudaError_t launch_gn_apply(const __nv_bfloat16* x0, int c0, const __nv_bfloat16
   if (ppb < 2 * step) ppb = 2 * step;
   const int slabs = static_cast<int>((hw + ppb - 1) / ppb);
   const dim3 grid(slabs, n);
-#define CA_GN(S, U)                                                                                                 \
-  gn_apply_kernel<S, U><<<grid, threads, 0, stream>>>(x0, c0, x1, c1, h, w, imgs_per_sample, groups, eps, sums, gamma, \
-                                                      beta, static_cast<int>(ppb), y)
+#define CA_GN(S, U)                                                                                               \
+  do {                                                                                                            \
+    auto kern = gn_apply_kernel<S, U>;                                                                            \
+    CA_KERNEL_LAUNCH(kern, grid, threads, 0, stream, x0, c0, x1, c1, h, w, imgs_per_sample, groups, eps, sums, gamma, \
+                     beta, static_cast<int>(ppb), y);                                                             \
+  } while (0)
   if (silu) {
     if (up2x) CA_GN(true, true); else CA_GN(true, false);
   } else {
@@ -235,6 +242,8 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  const __nv_bfloat16* __restrict__ add_rowvec, long long rows_per_vec,
                  __nv_bfloat16* __restrict__ y_sum, __nv_bfloat16* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
   const int warps_per_block = blockDim.x >> 5;
   const long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -331,10 +340,8 @@ cudaError_t launch_layernorm(const __nv_bfloat16* x, long long rows, int c, floa
   const int nv = ((c >> 3) + 31) / 32;
 #define CA_LN(NV)                                                                                                      \
   do {                                                                                                                 \
-    if (add_rowvec != nullptr)                                                                                         \
-      layernorm_kernel<NV, true><<<blocks, warps * 32, 0, stream>>>(x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y); \
-    else                                                                                                               \
-      layernorm_kernel<NV, false><<<blocks, warps * 32, 0, stream>>>(x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y); \
+    auto kern = (add_rowvec != nullptr) ? layernorm_kernel<NV, true> : layernorm_kernel<NV, false>;                   \
+    CA_KERNEL_LAUNCH(kern, blocks, warps * 32, 0, stream, x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y);    \
   } while (0)
   switch (nv) {
     case 1: CA_LN(1); break;
