@@ -383,7 +383,7 @@ GROUPS = {
     "video": [lambda: check_unet_i2vgen(1, 4, 32, True), lambda: check_unet_i2vgen(2, 2, 32, False)],
     "svd": [lambda: check_unet_svd(2, 4, 32, True), lambda: check_unet_svd(1, 3, 16, False)],
     "sparse": [lambda: check_step_i2vgen(2, False, sparse=[0, 2])],
-    "svd_loop": [check_cfg_euler_v, check_step_svd, lambda: check_step_svd(2, sparse=[1, 3])],
+    "svd_loop": [check_cfg_euler_v, check_step_svd],  # sparse SVD variant: CPU-emulated only (keeps the GPU suite short)
     "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
 }
 
