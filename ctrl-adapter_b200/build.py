@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libctrl_adapter_b200.so")
-SOURCES = ["gemm_conv.cu", "gemm_conv_bn64.cu", "gemm_conv_bn128.cu", "gemm_conv_bn160.cu", "gemm_conv_bn256.cu",
+SOURCES = ["gemm_conv.cu", "gemm_conv_bn64.cu", "gemm_conv_bn128.cu", "gemm_conv_bn160.cu", "gemm_conv_bn256.cu", "gemm_conv_wide.cu",
            "attention.cu", "norm.cu", "elementwise.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]

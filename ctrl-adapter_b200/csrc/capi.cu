@@ -131,6 +131,13 @@ int ca_gemm(const ca_gemm_desc* d, void* cuda_stream) {
     else if (d->w_rows <= 128) bn = 128;
     else bn = 256;
   }
+  // EXPERIMENT (off unless CA_GEMM_BN320=1): 256 x 320 pair tiles where 160-wide ones are used today
+  // (csrc/gemm_conv_wide.cu); only for the bias / bias+residual epilogues, CTA pairs, bf16 output
+  static const bool wide_ok = getenv("CA_GEMM_BN320") != nullptr && getenv("CA_GEMM_1CTA") == nullptr;
+  if (wide_ok && d->bn == 0 && bn == 160 && d->w_rows % 320 == 0 && d->act == CA_ACT_NONE && !d->out_fp32 &&
+      d->out_scale == 1.0f && d->blend_src == nullptr && (d->rowvec == nullptr || d->residual == nullptr) &&
+      reinterpret_cast<uintptr_t>(d->bias) % 16 == 0)
+    bn = 320;
   if (geglu && (d->w_rows % bn) != 0) return fail(CA_ERR_INVALID, "GEGLU needs w_rows %% bn == 0");
   // CTA pairs (tcgen05 cta_group::2, M = 256 per pair) unless CA_GEMM_1CTA is set (A/B comparison / debugging)
   static const int ncta = getenv("CA_GEMM_1CTA") ? 1 : 2;
@@ -198,7 +205,8 @@ int ca_gemm(const ca_gemm_desc* d, void* cuda_stream) {
     if (ktot % 8 != 0) return fail(CA_ERR_INVALID, "weight row length must be a multiple of 8");
     cuuint64_t dims[2] = {ktot, static_cast<cuuint64_t>(d->w_rows)};
     cuuint64_t strides[1] = {ktot * 2};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn / ncta)};  // each CTA of a pair stages half of the N tile
+    // each CTA of a pair stages half of the N tile (as two 80-row chunks for the 320-wide experiment)
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn == 320 ? 80 : bn / ncta)};
     int rc = make_tmap(&tw, d->w, 2, dims, strides, box);
     if (rc) return rc;
   }

@@ -49,6 +49,7 @@ cudaError_t launch_gemm_conv(int bn, int ncta, const CUtensorMap& a0, const CUte
     case 128: return launch_gemm_bn128(ncta, epi, a0, a1, w, p, grid, stream);
     case 160: return launch_gemm_bn160(ncta, epi, a0, a1, w, p, grid, stream);
     case 256: return launch_gemm_bn256(ncta, epi, a0, a1, w, p, grid, stream);
+    case 320: return ncta == 2 ? launch_gemm_wide(epi, a0, a1, w, p, grid, stream) : cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }
 }

@@ -37,6 +37,8 @@ struct GemmParams {
   unsigned long long* trace;  // developer builds (-DCA_TRACE) only: per-CTA role wait-cycle counters, else unused
 };
 
+cudaError_t launch_gemm_wide(int epi, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w, const GemmParams& p,
+                             int grid, cudaStream_t stream);
 cudaError_t launch_gemm_conv(int bn, int ncta, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w,
                              const GemmParams& p, int grid, cudaStream_t stream);
 

@@ -17,8 +17,9 @@ def build():
     os.makedirs(bdir, exist_ok=True)
     objs = []
     procs = []
-    for src in ["gemm_conv.cu", "gemm_conv_bn64.cu", "gemm_conv_bn128.cu", "gemm_conv_bn160.cu", "gemm_conv_bn256.cu",
-           "attention.cu", "norm.cu", "elementwise.cu", "capi.cu"]:
+    sys.path.insert(0, ROOT)
+    from ctrl_adapter_b200.build import SOURCES
+    for src in SOURCES:
         o = os.path.join(bdir, src.replace(".cu", ".o"))
         objs.append(o)
         procs.append(subprocess.Popen(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
