@@ -18,6 +18,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .persistence import PretrainedMixin
 from .layers import (BF16, BasicTransformerBlock, FeedForward, Attention, Linear, Norm, Packable, ResnetBlock2D,
                      TemporalConv, TimestepEmbedding)
 from .ops import ACT_NONE
@@ -255,7 +256,7 @@ class _ConfigDict(dict):
     __getattr__ = dict.__getitem__
 
 
-class ControlNetAdapter(nn.Module):
+class ControlNetAdapter(PretrainedMixin, nn.Module):
     """ctrl_adapter.py:12-224 (num_repeats == 1)."""
 
     config_name = "config.json"
@@ -350,31 +351,8 @@ class ControlNetAdapter(nn.Module):
             mid = as_nchw(self.mid_block_adapter.forward_nhwc(x, num_frames, t, ctx))
         return out, mid
 
-    # ---- minimal diffusers-style persistence (config.json + safetensors), diffusers itself is not required ----
-    def save_pretrained(self, path: str):
-        from safetensors.torch import save_file
-        os.makedirs(path, exist_ok=True)
-        with open(os.path.join(path, self.config_name), "w") as f:
-            json.dump({"_class_name": "ControlNetAdapter", **self.config}, f, indent=2)
-        save_file({k: v.contiguous() for k, v in self.state_dict().items()},
-                  os.path.join(path, "diffusion_pytorch_model.safetensors"))
 
-    @classmethod
-    def from_pretrained(cls, path: str, subfolder: Optional[str] = None, low_cpu_mem_usage=False, device_map=None,
-                        torch_dtype=None, **_kw):
-        from safetensors.torch import load_file
-        if subfolder:
-            path = os.path.join(path, subfolder)
-        if not os.path.isdir(path):
-            raise FileNotFoundError(f"{path}: only local model folders can be loaded (no network access)")
-        cfg = json.load(open(os.path.join(path, cls.config_name)))
-        cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}
-        m = cls(**cfg)
-        m.load_state_dict(load_file(os.path.join(path, "diffusion_pytorch_model.safetensors")))
-        return m.to(torch_dtype) if torch_dtype is not None else m
-
-
-class ControlNetRouter(nn.Module):
+class ControlNetRouter(PretrainedMixin, nn.Module):
     """model/ctrl_router.py:44-112.  The 13 routers' logits live in one [13, E] fp32 device table; masked softmax for
     all of them is one warp-shuffle kernel (one warp per router)."""
 

@@ -12,6 +12,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .persistence import PretrainedMixin
 from .adapter import _ConfigDict, as_nchw, timestep_vector, to_channels_last_bf16
 from .layers import BF16, Conv2d, ResnetBlock2D, TimestepEmbedding, Transformer2DModel
 from .ops import ACT_SILU
@@ -76,7 +77,7 @@ class _MidBlock(nn.Module):
         return self.resnets[1](x, temb_act)
 
 
-class ControlNetModel(nn.Module):
+class ControlNetModel(PretrainedMixin, nn.Module):
     def __init__(self, in_channels: int = 4, conditioning_channels: int = 3, flip_sin_to_cos: bool = True,
                  freq_shift: int = 0,
                  down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),

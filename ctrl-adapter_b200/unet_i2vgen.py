@@ -17,6 +17,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .persistence import PretrainedMixin
 from .adapter import _ConfigDict, timestep_vector, to_channels_last_bf16
 from .layers import (BF16, Attention, BasicTransformerBlock, Conv2d, FeedForward, Linear, Norm, Packable, ResnetBlock2D,
                      TemporalConv, TimestepEmbedding, Transformer2DModel)
@@ -197,7 +198,7 @@ class _ConvPad8(Conv2d):
         return w, b
 
 
-class I2VGenXLUNet(nn.Module):
+class I2VGenXLUNet(PretrainedMixin, nn.Module):
     def __init__(self, sample_size=None, in_channels: int = 4, out_channels: int = 4,
                  down_block_types=("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
                  up_block_types=("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),

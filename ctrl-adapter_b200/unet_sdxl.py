@@ -13,6 +13,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .persistence import PretrainedMixin
 from .adapter import _ConfigDict, as_nchw, timestep_vector, to_channels_last_bf16
 from .layers import BF16, Conv2d, Norm, ResnetBlock2D, TimestepEmbedding, Transformer2DModel
 
@@ -85,7 +86,7 @@ class _Up(nn.Module):
         return x
 
 
-class UNet2DConditionModel(nn.Module):
+class UNet2DConditionModel(PretrainedMixin, nn.Module):
     def __init__(self, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280),
                  transformer_layers_per_block=(1, 2, 10), attention_head_dim=(5, 10, 20), cross_attention_dim=2048,
                  addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816, norm_eps=1e-5,

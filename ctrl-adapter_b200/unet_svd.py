@@ -20,6 +20,7 @@ import torch
 from torch import nn
 
 from . import ops
+from .persistence import PretrainedMixin
 from .adapter import (AlphaBlender, TemporalBasicTransformerBlock, TemporalResnetBlock, _ConfigDict, timestep_vector,
                       to_channels_last_bf16)
 from .layers import BF16, BasicTransformerBlock, Conv2d, Linear, Norm, ResnetBlock2D, TimestepEmbedding
@@ -150,7 +151,7 @@ class _Up(nn.Module):
         return x
 
 
-class UNetSpatioTemporalConditionModel(nn.Module):
+class UNetSpatioTemporalConditionModel(PretrainedMixin, nn.Module):
     def __init__(self, sample_size=None, in_channels: int = 8, out_channels: int = 4,
                  down_block_types=("CrossAttnDownBlockSpatioTemporal", "CrossAttnDownBlockSpatioTemporal",
                                    "CrossAttnDownBlockSpatioTemporal", "DownBlockSpatioTemporal"),
@@ -173,11 +174,14 @@ class UNetSpatioTemporalConditionModel(nn.Module):
             # default (5, 10, 10, 20) would give the third stage 128-wide heads, which the frame-axis kernel does not do
             raise NotImplementedError("attention head dim must be 64: pass num_attention_heads=(5, 10, 20, 20) as the "
                                       "released stable-video-diffusion configs do")
-        self.config = _ConfigDict(in_channels=in_channels, out_channels=out_channels, num_frames=num_frames,
-                                  sample_size=sample_size, block_out_channels=tuple(block_out_channels),
-                                  cross_attention_dim=cross_attention_dim,
+        self.config = _ConfigDict(sample_size=sample_size, in_channels=in_channels, out_channels=out_channels,
+                                  down_block_types=tuple(down_block_types), up_block_types=tuple(up_block_types),
+                                  block_out_channels=tuple(block_out_channels),
                                   addition_time_embed_dim=addition_time_embed_dim,
-                                  projection_class_embeddings_input_dim=projection_class_embeddings_input_dim)
+                                  projection_class_embeddings_input_dim=projection_class_embeddings_input_dim,
+                                  layers_per_block=layers_per_block, cross_attention_dim=cross_attention_dim,
+                                  transformer_layers_per_block=transformer_layers_per_block,
+                                  num_attention_heads=heads, num_frames=num_frames)
         c0, c1, c2, c3 = block_out_channels
         temb = c0 * 4
         xd = cross_attention_dim

@@ -129,3 +129,63 @@ def test_adapter_save_load_roundtrip(tmp_path):
     assert m2.config == m.config
     for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
         assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_pretrained_folder_roundtrip(tmp_path):
+    """save_pretrained -> from_pretrained (config.json + safetensors / .bin) for the small boundary classes, and config
+    reconstruction of every class from its own saved configuration and from the published checkpoints' config.json."""
+    import json
+    import os
+    from ctrl_adapter_b200.controlnet import ControlNetModel
+    from ctrl_adapter_b200.unet_i2vgen import I2VGenXLUNet
+    from ctrl_adapter_b200.unet_sdxl import UNet2DConditionModel
+    from ctrl_adapter_b200.unet_svd import UNetSpatioTemporalConditionModel
+    r = A.ControlNetRouter(**cases.ROUTER_KW)
+    for safe in (True, False):
+        d = str(tmp_path / f"router{int(safe)}")
+        r.save_pretrained(d, safe_serialization=safe)
+        assert json.load(open(os.path.join(d, "config.json")))["_class_name"] == "ControlNetRouter"
+        r2 = A.ControlNetRouter.from_pretrained(str(tmp_path), subfolder=f"router{int(safe)}", low_cpu_mem_usage=False,
+                                                device_map=None)
+        assert r2.router_type == r.router_type and r2.num_experts == r.num_experts
+        for (k1, v1), (k2, v2) in zip(r.state_dict().items(), r2.state_dict().items()):
+            assert k1 == k2 and torch.equal(v1, v2)
+    with pytest.raises(FileNotFoundError):
+        A.ControlNetRouter.from_pretrained(str(tmp_path / "missing"))
+    # published config.json contents (abridged to the keys that matter + a few the classes must tolerate)
+    published = {
+        ControlNetModel: dict(_class_name="ControlNetModel", _diffusers_version="0.16.0.dev0", act_fn="silu",
+                              attention_head_dim=8, block_out_channels=[320, 640, 1280, 1280], class_embed_type=None,
+                              conditioning_embedding_out_channels=[16, 32, 96, 256],
+                              controlnet_conditioning_channel_order="rgb", cross_attention_dim=768,
+                              down_block_types=["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"], downsample_padding=1,
+                              flip_sin_to_cos=True, freq_shift=0, in_channels=4, layers_per_block=2,
+                              mid_block_scale_factor=1, norm_eps=1e-05, norm_num_groups=32, num_class_embeds=None,
+                              only_cross_attention=False, projection_class_embeddings_input_dim=None,
+                              resnet_time_scale_shift="default", upcast_attention=False, use_linear_projection=False),
+        UNet2DConditionModel: dict(_class_name="UNet2DConditionModel", act_fn="silu", addition_embed_type="text_time",
+                                   addition_time_embed_dim=256, attention_head_dim=[5, 10, 20],
+                                   block_out_channels=[320, 640, 1280], cross_attention_dim=2048, in_channels=4,
+                                   out_channels=4, projection_class_embeddings_input_dim=2816, sample_size=128,
+                                   transformer_layers_per_block=[1, 2, 10], use_linear_projection=True,
+                                   down_block_types=["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"]),
+        I2VGenXLUNet: dict(_class_name="I2VGenXLUNet", attention_head_dim=64, block_out_channels=[320, 640, 1280, 1280],
+                           cross_attention_dim=1024, in_channels=4, out_channels=4, layers_per_block=2,
+                           norm_num_groups=32, num_attention_heads=None, sample_size=32,
+                           down_block_types=["CrossAttnDownBlock3D"] * 3 + ["DownBlock3D"],
+                           up_block_types=["UpBlock3D"] + ["CrossAttnUpBlock3D"] * 3),
+        UNetSpatioTemporalConditionModel: dict(_class_name="UNetSpatioTemporalConditionModel", addition_time_embed_dim=256,
+                                               block_out_channels=[320, 640, 1280, 1280], cross_attention_dim=1024,
+                                               in_channels=8, layers_per_block=2, num_attention_heads=[5, 10, 20, 20],
+                                               num_frames=14, out_channels=4, projection_class_embeddings_input_dim=768,
+                                               sample_size=96, transformer_layers_per_block=1,
+                                               down_block_types=["CrossAttnDownBlockSpatioTemporal"] * 3 +
+                                               ["DownBlockSpatioTemporal"],
+                                               up_block_types=["UpBlockSpatioTemporal"] +
+                                               ["CrossAttnUpBlockSpatioTemporal"] * 3),
+    }
+    with torch.device("meta"):
+        for cls, cfg in published.items():
+            m = cls.from_config(cfg)
+            m2 = cls.from_config(json.loads(json.dumps({"_class_name": cls.__name__, **dict(m.config)}, default=list)))
+            assert set(m.state_dict()) == set(m2.state_dict())
