@@ -100,6 +100,14 @@ def test_emulated_unet_svd():
     o, p = _pair(lambda: O(**cases.UNET_SVD_KW), lambda: UNetSpatioTemporalConditionModel(**cases.UNET_SVD_KW), 8)
     _compare(o, p, cases.unet_svd_inputs(2, 3, 16, with_residuals=True, chans=(320, 640, 1280, 1280), ctx=1024))
     _compare(o, p, cases.unet_svd_inputs(1, 2, 16, with_residuals=False, chans=(320, 640, 1280, 1280), ctx=1024))
+    # non-square latents (the 576 x 1024 configuration is 72 x 128): 16 x 24 here
+    inp = cases.unet_svd_inputs(1, 2, 16, with_residuals=True, chans=(320, 640, 1280, 1280), ctx=1024)
+    inp["sample"] = torch.cat([inp["sample"], inp["sample"][..., :8]], dim=-1)
+    inp["down_block_additional_residuals"] = [torch.cat([t, t[..., : t.shape[-1] // 2]], dim=-1)
+                                              for t in inp["down_block_additional_residuals"]]
+    m = inp["mid_block_additional_residual"]
+    inp["mid_block_additional_residual"] = torch.cat([m, m[..., : m.shape[-1] // 2]], dim=-1)
+    _compare(o, p, inp)
 
 
 @pytest.mark.slow
@@ -116,6 +124,52 @@ def test_emulated_unet_sdxl():
     from oracle.unet_sdxl import UNet2DConditionModel as O
     o, p = _pair(lambda: O(), lambda: UNet2DConditionModel(), 6)
     _compare(o, p, cases.unet_sdxl_inputs(2, 16, with_residuals=True))
+
+
+@pytest.mark.slow
+def test_emulated_i2vgen_loop_multi_controlnet_router():
+    """One I2VGen-XL iteration with TWO ControlNets run through MultiControlNetModel, the router's masked softmax and
+    the weighted merge (incl. the w[e // F] indexing quirk) vs the restated reference loop."""
+    from ctrl_adapter_b200.adapter import ControlNetAdapter, ControlNetRouter
+    from ctrl_adapter_b200.controlnet import ControlNetModel, MultiControlNetModel
+    from ctrl_adapter_b200.pipeline_i2vgen import I2VGenXLControlNetAdapterLoop
+    from ctrl_adapter_b200.unet_i2vgen import I2VGenXLUNet
+    from oracle.adapter import ControlNetAdapter as OA, ControlNetRouter as OR
+    from oracle.controlnet import ControlNetModel as OC, MultiControlNetModel as OM
+    from oracle.pipeline_i2vgen import DDIMScheduler, i2vgen_step
+    from oracle.unet_i2vgen import I2VGenXLUNet as OU
+    from oracle.weights import seeded_tensor
+    b, f, r = 1, 4, 16
+    n = 2 * b * f
+    kw = dict(cases.ADAPTER_VIDEO_KW, num_frames=f)
+    oad, ad = _pair(lambda: OA(**kw), lambda: ControlNetAdapter(**kw), 2)
+    oun, un = _pair(lambda: OU(), lambda: I2VGenXLUNet(), 7)
+    nets = [_pair(lambda: OC(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 40 + k) for k in range(2)]
+    ocn, cn = OM([p_[0] for p_ in nets]), MultiControlNetModel([p_[1] for p_ in nets])
+    rk = dict(cases.ROUTER_KW, num_experts=3)
+    orouter = seeded_init_(OR(**rk), 3).eval()
+    router = ControlNetRouter(**rk)
+    router.load_state_dict(orouter.state_dict())
+    masks = [1, 1, 0]
+    images = [_q(torch.sigmoid(seeded_tensor(f"v_img{k}", (n, 3, 8 * r, 8 * r)))) for k in range(2)]
+    inp = dict(latents=seeded_tensor("v_lat", (b, 4, f, r, r)), prompt_embeds=seeded_tensor("v_pe", (2 * b, 77, 1024)),
+               image_latents=seeded_tensor("v_il", (2 * b, 4, f, r, r)),
+               image_embeddings=seeded_tensor("v_ie", (2 * b, 1, 1024)), fps=torch.tensor([16.0] * (2 * b)),
+               controlnet_prompt_embeds=seeded_tensor("v_cpe", (n, 77, 768)))
+    inp = {k: _q(v) for k, v in inp.items()}
+    sch = DDIMScheduler()
+    sch.set_timesteps(50)
+    with emu.patched_ops():
+        loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, router, num_inference_steps=50, guidance_scale=9.0,
+                                             inference_expert_masks=masks)
+        loop.prepare(control_images=images, **inp)
+        lat = i2vgen_step(ocn, oad, oun, sch, 0, inp["latents"], inp["prompt_embeds"], inp["image_latents"],
+                          inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"], images, router=orouter,
+                          masks=masks)
+        loop.step(0)
+    ours = loop.latents_bcfhw().float()
+    rel = float((ours - lat).norm() / lat.norm())
+    assert rel <= 2e-2, rel
 
 
 @pytest.mark.slow
