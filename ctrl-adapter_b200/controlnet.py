@@ -6,6 +6,7 @@ Same constructor kwargs (default SD1.5 topology), forward signature (including t
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple, Union
 
 import torch
@@ -31,10 +32,15 @@ class ControlNetConditioningEmbedding(nn.Module):
             self.blocks.append(Conv2d(cin, cout, 3, stride=2))
         self.conv_out = Conv2d(block_out_channels[-1], out_channels, 3)
 
+    # EXPERIMENT (off unless CA_FOLD_SMALL_CONV=1; CPU-verified through the op-layer emulation, no hardware run yet): the
+    # 8- and 16-channel stride-1 convolutions at full image resolution run with 4-8 adjacent pixels folded into the
+    # channel axis (layers.Conv2d.forward_folded) instead of padding every tap to 64 channels
     def forward(self, cond_nhwc8, residual):
-        e = self.conv_in(cond_nhwc8, act=ACT_SILU)
+        fold = os.environ.get("CA_FOLD_SMALL_CONV") == "1"
+        conv = (lambda m, x, **kw: m.forward_folded(x, **kw)) if fold else (lambda m, x, **kw: m(x, **kw))
+        e = conv(self.conv_in, cond_nhwc8, act=ACT_SILU)
         for blk in self.blocks:
-            e = blk(e, act=ACT_SILU)
+            e = conv(blk, e, act=ACT_SILU) if blk.stride == 1 else blk(e, act=ACT_SILU)
         return self.conv_out(e, residual=residual)  # sample + controlnet_cond (controlnet.py:817) fused
 
 

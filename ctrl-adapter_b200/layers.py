@@ -96,6 +96,49 @@ class Conv2d(Packable):
         w, b = self.packed()
         return ops.conv2d(x, w, b, ksize=self.k, stride=self.stride, x2=x2, **kw)
 
+    # ---- small-channel 3x3 convolutions: fold F adjacent pixels of a row into the channel axis ----------------------
+    # The tensor-core kernel contracts 64 channels per tap; with C = 8 or 16 (ControlNet conditioning embedding at
+    # 512 x 512) 7/8 or 3/4 of every MMA and of every staged tile is zero padding.  Viewing [N, H, W, C] as
+    # [N, H, W/F, F*C] (the same memory) turns the layer into a 3x3 convolution with F*C = 64 input and F*Cout output
+    # channels whose weight is block-banded:  W'[(jo, co), dy, dq, (ji, ci)] = W[co, ci, dy, dx]  with
+    # dx = F*dq + ji - jo  in {-1, 0, 1}, zero otherwise.  Same arithmetic (zeros added), 4x fewer MMAs and staged bytes
+    # per pixel, no kernel change; zero padding at the row ends is the folded image's own zero padding.
+    def fold_factor(self, x) -> int:
+        cs = x.shape[3]
+        if self.k != 3 or self.stride != 1 or cs not in (8, 16, 32) or cs < self.cin:
+            return 1
+        f = 64 // cs
+        return f if (x.shape[2] % f == 0 and (f * self.cout) % 8 == 0) else 1
+
+    def packed_folded(self, f: int, cs: int):
+        key = (self._key(), f, cs)
+        cache = getattr(self, "_fold_cache", None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                w = self.weight.detach().float()                      # [Cout, Cin, 3, 3] (dy, dx)
+                cout, cin = w.shape[:2]
+                wf = torch.zeros(f, cout, f, cs, 3, 3, dtype=torch.float32, device=w.device)  # [jo, co, ji, ci, dy, dq]
+                for jo in range(f):
+                    for ji in range(f):
+                        for dq in (-1, 0, 1):
+                            dx = f * dq + ji - jo
+                            if -1 <= dx <= 1:
+                                wf[jo, :, ji, :cin, :, dq + 1] = w[:, :, :, dx + 1]
+                wf = wf.reshape(f * cout, f * cs, 3, 3)
+                bias = self.bias.detach().repeat(f)
+                self._fold_cache = (key, ops.pack_conv_weight(wf, 8), _f32(bias))
+        return self._fold_cache[1], self._fold_cache[2]
+
+    def forward_folded(self, x, **kw):
+        """x [N, H, W, Cs] -> [N, H, W, Cout]; falls back to forward() when the layer / shape does not qualify."""
+        f = self.fold_factor(x)
+        if f == 1:
+            return self.forward(x, **kw)
+        n, h, w_, cs = x.shape
+        wp, bp = self.packed_folded(f, cs)
+        y = ops.conv2d(x.reshape(n, h, w_ // f, f * cs), wp, bp, ksize=3, stride=1, **kw)
+        return y.reshape(n, h, w_, self.cout)
+
 
 class TemporalConv(Packable):
     """Conv3d (3,1,1) container (weight [Cout, Cin, 3, 1, 1])."""

@@ -15,6 +15,7 @@ Stand-alone report:  python -m tests.module_checks [--group adapter|controlnet|u
 from __future__ import annotations
 
 import json
+import os
 import sys
 import time
 
@@ -376,6 +377,15 @@ def check_step_svd(steps=2, sparse=None):
                     tol_rel=2e-2, tol_max=8e-2)
 
 
+def check_controlnet_folded():
+    """ControlNet with CA_FOLD_SMALL_CONV=1 (conditioning-embedding convolutions with pixels folded into channels)."""
+    os.environ["CA_FOLD_SMALL_CONV"] = "1"
+    try:
+        return check_controlnet(2, 16)
+    finally:
+        os.environ.pop("CA_FOLD_SMALL_CONV", None)
+
+
 GROUPS = {
     "adapter": [lambda: check_adapter("sdxl", 2, 8), lambda: check_adapter("video", 1, 8, 4), check_router],
     "controlnet": [lambda: check_controlnet(2, 8), lambda: check_controlnet(2, 16, True, 0.75)],
@@ -383,6 +393,7 @@ GROUPS = {
     "video": [lambda: check_unet_i2vgen(1, 4, 32, True), lambda: check_unet_i2vgen(2, 2, 32, False)],
     "svd": [lambda: check_unet_svd(2, 4, 32, True), lambda: check_unet_svd(1, 3, 16, False)],
     "sparse": [lambda: check_step_i2vgen(2, False, sparse=[0, 2])],
+    "fold": [check_controlnet_folded],
     "svd_loop": [check_cfg_euler_v, check_step_svd],  # sparse SVD variant: CPU-emulated only (keeps the GPU suite short)
     "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
 }

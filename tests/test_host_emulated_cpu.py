@@ -91,6 +91,34 @@ def test_emulated_controlnet():
     _compare(o, p, dict(cases.controlnet_inputs(2, 8), conditioning_scale=0.75))
 
 
+def test_emulated_controlnet_folded_small_convs(monkeypatch):
+    """CA_FOLD_SMALL_CONV=1: the 8 / 16 / 32-channel stride-1 convolutions of the conditioning embedding run with adjacent
+    pixels folded into the channel axis (block-banded weights); the ControlNet output must not change."""
+    from ctrl_adapter_b200.controlnet import ControlNetModel
+    from ctrl_adapter_b200.layers import Conv2d
+    from oracle.controlnet import ControlNetModel as O
+    o, p = _pair(lambda: O(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 4)
+    inputs = dict(cases.controlnet_inputs(2, 8), conditioning_scale=1.0)
+    calls = []
+    orig = Conv2d.forward_folded
+
+    def spy(self, x, **kw):
+        calls.append((self.cin, self.cout, self.fold_factor(x)))
+        return orig(self, x, **kw)
+    monkeypatch.setattr(Conv2d, "forward_folded", spy)
+    monkeypatch.setenv("CA_FOLD_SMALL_CONV", "1")
+    _compare(o, p, inputs)
+    assert (3, 16, 8) in calls and (16, 16, 4) in calls and (32, 32, 2) in calls, calls
+    # and layer-level: folded == unfolded to bf16 rounding on a ragged-free random case
+    torch.manual_seed(0)
+    c = Conv2d(16, 16, 3).to(BF16)
+    x = torch.randn(2, 12, 16, 16).to(BF16)
+    with emu.patched_ops():
+        a = c(x, act=1).float()
+        b = c.forward_folded(x, act=1).float()
+    assert float((a - b).abs().max()) <= 2.0 ** -7 * float(a.abs().max())
+
+
 @pytest.mark.slow
 def test_emulated_unet_svd():
     """Two clips with DIFFERENT image tokens + 5-D residuals with surplus entries: covers the per-clip broadcast rows and
