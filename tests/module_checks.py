@@ -377,6 +377,22 @@ def check_step_svd(steps=2, sparse=None):
                     tol_rel=2e-2, tol_max=8e-2)
 
 
+def check_extra_shapes():
+    """Kernel-level checks at shapes that first appear with the SVD / folded-conv / wide-tile work (576 x 1024 video ->
+    72 x 128 latents and its 36 x 64, 18 x 32 levels; K/V projection shape; folded conditioning convolutions)."""
+    from tests import kernel_checks as kc
+    kc.RESULTS.clear()
+    recs = [kc.check_attention(1, 5, 2304, 2304, 64), kc.check_attention(2, 10, 576, 576, 64),
+            kc.check_attention(2, 20, 144, 144, 64), kc.check_temporal_attention(2, 14, 144, 10),
+            kc.check_conv(2, 36, 64, 320, 320, out_fp32=False, residual=True),
+            kc.check_conv(2, 18, 32, 640, 640, out_fp32=False, rowvec=True),
+            kc.check_conv(2, 64, 16, 64, 128, out_fp32=False), kc.check_conv(1, 64, 32, 64, 64, out_fp32=False),
+            kc.check_linear(1232, 2048, 2560, out_fp32=False), kc.check_linear(4608, 320, 960, out_fp32=False)]
+    for r in recs:
+        RESULTS.append(r)
+    return recs
+
+
 def check_controlnet_folded():
     """ControlNet with CA_FOLD_SMALL_CONV=1 (conditioning-embedding convolutions with pixels folded into channels)."""
     os.environ["CA_FOLD_SMALL_CONV"] = "1"
@@ -394,6 +410,7 @@ GROUPS = {
     "svd": [lambda: check_unet_svd(2, 4, 32, True), lambda: check_unet_svd(1, 3, 16, False)],
     "sparse": [lambda: check_step_i2vgen(2, False, sparse=[0, 2])],
     "fold": [check_controlnet_folded],
+    "shapes": [check_extra_shapes],
     "svd_loop": [check_cfg_euler_v, check_step_svd],  # sparse SVD variant: CPU-emulated only (keeps the GPU suite short)
     "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
 }

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("group", ["svd", "sparse", "svd_loop", "fold"])
+@pytest.mark.parametrize("group", ["shapes", "svd", "sparse", "svd_loop", "fold"])
 def test_pending_first_hardware_run(group):
     if not torch.cuda.is_available():
         pytest.fail("GPU tests selected but no CUDA device is visible (there is no CPU fallback to test)")
