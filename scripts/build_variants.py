@@ -3,6 +3,8 @@ CA_B200_LIB=<path>, see ctrl-adapter_b200/_lib.py).  Runs on the CPU box (nvcc c
 
   python scripts/build_variants.py pdl      -> ctrl-adapter_b200/libctrl_adapter_b200_pdl.so    (-DCA_PDL)
   python scripts/build_variants.py trace    -> ctrl-adapter_b200/libctrl_adapter_b200_trace.so  (-DCA_TRACE)
+  python scripts/build_variants.py epi      -> ..._epi.so  (-DCA_EXP_EPI: GEMM epilogue bias loads hoisted ahead of the TMEM wait)
+  python scripts/build_variants.py all      -> ..._all.so  (-DCA_PDL -DCA_EXP_EPI)
 
 A/B on the B200:   python bench.py --steps 10 ...   vs   CA_B200_LIB=$PWD/ctrl-adapter_b200/libctrl_adapter_b200_pdl.so python bench.py ...
 """
@@ -13,7 +15,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "ctrl-adapter_b200")
 sys.path.insert(0, ROOT)
-VARIANTS = {"pdl": ["-DCA_PDL"], "trace": ["-DCA_TRACE"], "pdl_trace": ["-DCA_PDL", "-DCA_TRACE"]}
+VARIANTS = {"pdl": ["-DCA_PDL"], "trace": ["-DCA_TRACE"], "pdl_trace": ["-DCA_PDL", "-DCA_TRACE"],
+            "epi": ["-DCA_EXP_EPI"], "all": ["-DCA_PDL", "-DCA_EXP_EPI"]}
 
 
 def build(name):
