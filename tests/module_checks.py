@@ -439,6 +439,15 @@ def run(group=None):
 
 
 if __name__ == "__main__":
+    if "--groups" in sys.argv:  # several groups in one process; per-group verdicts in the JSON (tests/test_zz_svd_gpu.py)
+        names = sys.argv[sys.argv.index("--groups") + 1].split(",")
+        verdict = {}
+        for gname in names:
+            res = [dict(r) for r in run(gname)]
+            verdict[gname] = {"ok": all(r["ok"] for r in res), "results": res}
+        if "--json" in sys.argv:
+            json.dump(verdict, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1, default=str)
+        sys.exit(0 if all(v["ok"] for v in verdict.values()) else 1)
     grp = sys.argv[sys.argv.index("--group") + 1] if "--group" in sys.argv else None
     res = run(grp)
     if "--json" in sys.argv:

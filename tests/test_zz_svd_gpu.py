@@ -8,6 +8,7 @@ no hardware run when it was written (the round's GPU budget was spent).  Until i
 its own process, and a failure is reported as xfail instead of red so that it cannot mask the validated suites; a pass
 shows up as a normal pass.  Remove the xfail path once a green run is recorded in DESIGN.md.
 """
+import json
 import os
 import subprocess
 import sys
@@ -17,15 +18,32 @@ import torch
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GROUPS = ["shapes", "svd", "sparse", "svd_loop", "fold"]
 
 
-@pytest.mark.parametrize("group", ["shapes", "svd", "sparse", "svd_loop", "fold"])
-def test_pending_first_hardware_run(group):
+@pytest.fixture(scope="module")
+def pending_results(tmp_path_factory):
+    """All pending groups in ONE child process (one interpreter / torch start-up); a crash or CUDA fault there cannot
+    poison this process's context."""
     if not torch.cuda.is_available():
         pytest.fail("GPU tests selected but no CUDA device is visible (there is no CPU fallback to test)")
-    r = subprocess.run([sys.executable, "-m", "tests.module_checks", "--group", group], cwd=ROOT, capture_output=True,
-                       text=True, timeout=900)
-    tail = (r.stdout + r.stderr)[-3000:]
-    print(tail)
-    if r.returncode != 0 or "[FAIL]" in r.stdout:
-        pytest.xfail(f"{group}: first hardware run did not pass -- " + tail[-800:])
+    out = str(tmp_path_factory.mktemp("pending") / "pending.json")
+    try:
+        r = subprocess.run([sys.executable, "-m", "tests.module_checks", "--groups", ",".join(GROUPS), "--json", out],
+                           cwd=ROOT, capture_output=True, text=True, timeout=1200)
+        log = (r.stdout + r.stderr)[-6000:]
+    except subprocess.TimeoutExpired as e:  # pragma: no cover
+        log = "timeout: " + str(e)[-2000:]
+    print(log)
+    verdict = json.load(open(out)) if os.path.exists(out) else {}
+    return verdict, log
+
+
+@pytest.mark.parametrize("group", GROUPS)
+def test_pending_first_hardware_run(group, pending_results):
+    verdict, log = pending_results
+    if group not in verdict:
+        pytest.xfail(f"{group}: the pending-checks process did not get this far -- " + log[-600:])
+    if not verdict[group]["ok"]:
+        bad = [r for r in verdict[group]["results"] if not r.get("ok")]
+        pytest.xfail(f"{group}: first hardware run did not pass -- " + json.dumps(bad, default=str)[:800])
