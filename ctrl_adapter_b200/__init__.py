@@ -1,7 +1,6 @@
-"""Importable alias of the ``ctrl-adapter_b200/`` package directory (a hyphen is not a valid module name)."""
-import os as _os
+"""ctrl_adapter_b200: B200-native (sm_100a) denoising hot path of Ctrl-Adapter.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "ctrl-adapter_b200")
-__path__.insert(0, _real)
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+The package directory is ``ctrl_adapter_b200/`` (``ctrl-adapter_b200`` at the repository root is a symlink to it, kept
+for the repository naming).
+"""
+__version__ = "0.2.0"

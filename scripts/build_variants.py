@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PKG = os.path.join(ROOT, "ctrl-adapter_b200")
+PKG = os.path.join(ROOT, "ctrl_adapter_b200")
 sys.path.insert(0, ROOT)
 VARIANTS = {"pdl": ["-DCA_PDL"], "trace": ["-DCA_TRACE"], "pdl_trace": ["-DCA_PDL", "-DCA_TRACE"],
             "epi": ["-DCA_EXP_EPI"], "all": ["-DCA_PDL", "-DCA_EXP_EPI"]}

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PKG = os.path.join(ROOT, "ctrl-adapter_b200")
+PKG = os.path.join(ROOT, "ctrl_adapter_b200")
 TRACE_LIB = os.path.join(PKG, "libctrl_adapter_b200_trace.so")
 
 

@@ -57,7 +57,7 @@ def test_fails_loudly_without_gpu(lib):
 
 
 def test_product_never_imports_oracle():
-    pkg = os.path.join(ROOT, "ctrl-adapter_b200")
+    pkg = os.path.join(ROOT, "ctrl_adapter_b200")
     for f in os.listdir(pkg):
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
