@@ -204,6 +204,11 @@ class Attention(Packable):
         self.to_k = nn.Linear(cd, inner, bias=False)
         self.to_v = nn.Linear(cd, inner, bias=False)
         self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+        self._static_kv = None   # (ctx object, ctx._version, weight key, projected K/V) -- see cache_static_context()
+        self._static_cv = None   # same for the single-token output vector
+
+    def _static_hit(self, slot, ctx):
+        return slot is not None and slot[0] is ctx and slot[1] == ctx._version and slot[2] == self._key()
 
     def _pad_rows(self, w):  # [heads*d, K] -> [heads*dp, K]
         d, dp = self.dim_head, _pad64(self.dim_head)
@@ -236,7 +241,9 @@ class Attention(Packable):
         if self.is_cross:
             q = ops.linear(x.reshape(b * l, dq), pk["wq"]).reshape(b, l, inner)
             if kv is None:
-                kv = self.project_kv(ctx)
+                # step-invariant context (the prompt embedding of a denoising loop): projected once, see
+                # cache_static_context(); any other tensor object / in-place update / weight change misses
+                kv = self._static_kv[3] if self._static_hit(self._static_kv, ctx) else self.project_kv(ctx)
             k, v = kv[:, :, :inner], kv[:, :, inner:]
         else:
             qkv = ops.linear(x.reshape(b * l, dq), pk["wqkv"]).reshape(b, l, 3 * inner)
@@ -246,16 +253,47 @@ class Attention(Packable):
                          residual=None if residual is None else residual.reshape(b * l, dq))
         return out.reshape(b, l, dq)
 
-    def single_token_output(self, ctx_vec):
+    def single_token_output(self, ctx_vec, src=None):
         """Cross attention over ONE key/value token: softmax == 1, so every query receives to_out(to_v(ctx)).
-        ctx_vec [1, Dc] -> [1, D] (exact, including the bf16 rounding points of the SDPA path)."""
+        ctx_vec [1, Dc] -> [1, D] (exact, including the bf16 rounding points of the SDPA path).  `src` is the tensor
+        object ctx_vec was sliced from: when it is the cached step-invariant context the stored vector is returned."""
+        if src is not None and self._static_hit(self._static_cv, src) and self._static_cv[3].shape[0] == ctx_vec.shape[0]:
+            return self._static_cv[3]
         pk = self.packed()
         return ops.linear(ops.linear(ctx_vec, pk["wv"]), pk["wo"], pk["bo"])
+
+    def cache_static(self, ctx, ctx_vec=None):
+        """Projects a step-invariant context once (K/V for the attention kernel, or the single-token output vector)."""
+        if ctx_vec is not None:
+            self._static_cv = None
+            self._static_cv = (ctx, ctx._version, self._key(), self.single_token_output(ctx_vec))
+        else:
+            self._static_kv = (ctx, ctx._version, self._key(), self.project_kv(ctx))
 
     def project_kv(self, ctx):
         pk = self.packed()
         b, lk, dc = ctx.shape
         return ops.linear(ctx.reshape(b * lk, dc), pk["wkv"]).reshape(b, lk, -1)
+
+
+def cache_static_context(root: nn.Module, ctx: torch.Tensor, single_token_rows: Optional[int] = None):
+    """The cross-attention context of a denoising loop does not depend on the timestep or the latents, so its K/V
+    projections are step-invariant (the reference recomputes them every step: e.g. attention_processor to_k / to_v
+    under sdxl_controlnet_adapter_pipeline.py:1356).  This projects `ctx` once for every cross attention under `root`
+    whose key width matches; forward() then uses the stored tensors whenever it is handed this very tensor object
+    unmodified (identity + version check), and recomputes for anything else.  Exact: same kernels, same operands.
+    `single_token_rows`: for single-token contexts, the number of leading rows the consumer slices ([:1] or [:B])."""
+    if ctx.dtype != BF16 or not ctx.is_contiguous():
+        raise ValueError("cache_static_context expects the bf16 contiguous tensor that will be passed to forward()")
+    n = 0
+    for m in root.modules():
+        if isinstance(m, Attention) and m.is_cross and m.to_k.weight.shape[1] == ctx.shape[-1]:
+            if single_token_rows is not None:
+                m.cache_static(ctx, ctx.reshape(-1, ctx.shape[-1])[:single_token_rows].contiguous())
+            else:
+                m.cache_static(ctx)
+            n += 1
+    return n
 
 
 class GEGLUProj(Packable):
