@@ -110,7 +110,7 @@ class TemporalBasicTransformerBlock(nn.Module):
         self.norm3 = Norm(dim, 1e-5)
         self.ff = FeedForward(dim)
 
-    def forward(self, h, emb, frames: int, hw: int, ctx_vec, blend_src=None, blend_alpha=None):
+    def forward(self, h, emb, frames: int, hw: int, ctx_vec, blend_src=None, blend_alpha=None, ctx_src=None):
         """h [B*F*HW, D]; emb [B*F, D] frame-position embedding added first (adapter_spatial_temporal.py:279);
         ctx_vec [1, Dc] (or [B, Dc], one per clip): single-token context (cross attention over one key collapses to
         to_out(to_v(ctx)))."""
@@ -124,7 +124,7 @@ class TemporalBasicTransformerBlock(nn.Module):
         o = ops.temporal_attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], clips, frames, hw,
                                    self.heads, 0.125, row_stride=3 * inner)
         x = ops.linear(o, pk["wo"], pk["bo"], residual=x)
-        cv = self.attn2.single_token_output(ctx_vec)  # [1, D], or one row per clip ([B, D]: SVD backbone)
+        cv = self.attn2.single_token_output(ctx_vec, src=ctx_src)  # [1, D], or one row per clip ([B, D]: SVD backbone)
         rpv = rows
         if cv.shape[0] > 1:
             # diffusers quirk kept by the reference (transformer_temporal.py / adapter_spatial_temporal.py:247-250):
@@ -223,7 +223,7 @@ class AdapterSpatioTemporal(nn.Module):
             if ctx.shape[1] == 1:
                 # single-token context (video path, i2vgen pipeline :1048): cross attention == broadcast vector
                 hcur = blk.attn1(blk.norm1.layer_norm(hcur), residual=hcur)
-                cv = blk.attn2.single_token_output(ctx.reshape(-1, ctx.shape[-1])[:1].contiguous())
+                cv = blk.attn2.single_token_output(ctx.reshape(-1, ctx.shape[-1])[:1].contiguous(), src=ctx)
                 n3, hsum = blk.norm3.layer_norm(hcur.reshape(n * hw, -1), add_rowvec=cv, rows_per_vec=n * hw,
                                                 return_sum=True)
                 hs = blk.ff(n3, residual=hsum)
@@ -235,7 +235,7 @@ class AdapterSpatioTemporal(nn.Module):
                 emb = self.transformer_time_embedding(ops.timestep_embedding(frames_idx, c))  # [N, 512]
                 hs = self.temporal_attentions[i](hs, emb, num_frames, hw,
                                                  ctx.reshape(-1, ctx.shape[-1])[:1].contiguous(), blend_src=hs,
-                                                 blend_alpha=self.transformers_time_mixer[i].alpha())
+                                                 blend_alpha=self.transformers_time_mixer[i].alpha(), ctx_src=ctx)
             x = self.proj_out(hs, residual=x.reshape(n * hw, c)).reshape(n, h, w, c)
         return x
 
@@ -350,6 +350,17 @@ class ControlNetAdapter(PretrainedMixin, nn.Module):
             x = to_channels_last_bf16(mid_block_res_sample)
             mid = as_nchw(self.mid_block_adapter.forward_nhwc(x, num_frames, t, ctx))
         return out, mid
+
+
+    @torch.no_grad()
+    def forward_mid(self, mid_block_res_sample, num_frames=None, timestep=None, encoder_hidden_states=None):
+        """Only the mid-block adapter of forward() (the loops use it on the steps whose conditioning scale is 0: the
+        reference then discards the down-block outputs but still injects the mid one, i2vgen pipeline :1083)."""
+        if mid_block_res_sample is None or self.mid_block_adapter is None:
+            return None
+        x = to_channels_last_bf16(mid_block_res_sample)
+        t = timestep_vector(timestep, x.shape[0], x.device)
+        return as_nchw(self.mid_block_adapter.forward_nhwc(x, num_frames, t, _prep_ctx(encoder_hidden_states)))
 
 
 class ControlNetRouter(PretrainedMixin, nn.Module):

@@ -32,16 +32,16 @@ class ControlNetConditioningEmbedding(nn.Module):
             self.blocks.append(Conv2d(cin, cout, 3, stride=2))
         self.conv_out = Conv2d(block_out_channels[-1], out_channels, 3)
 
-    # EXPERIMENT (off unless CA_FOLD_SMALL_CONV=1; CPU-verified through the op-layer emulation, no hardware run yet): the
-    # 8- and 16-channel stride-1 convolutions at full image resolution run with 4-8 adjacent pixels folded into the
-    # channel axis (layers.Conv2d.forward_folded) instead of padding every tap to 64 channels
-    def forward(self, cond_nhwc8, residual):
-        fold = os.environ.get("CA_FOLD_SMALL_CONV") == "1"
+    # the 8- / 16- / 32-channel stride-1 convolutions at full image resolution run with 8 / 4 / 2 adjacent pixels folded
+    # into the channel axis (layers.Conv2d.forward_folded) instead of padding every tap to 64 channels; GPU-verified in
+    # round 2 (profiles/r2_parity.md, group `fold`; -1.3 ms / SDXL step).  CA_FOLD_SMALL_CONV=0 restores the padded form.
+    def forward(self, cond_nhwc8):
+        fold = os.environ.get("CA_FOLD_SMALL_CONV", "1") != "0"
         conv = (lambda m, x, **kw: m.forward_folded(x, **kw)) if fold else (lambda m, x, **kw: m(x, **kw))
         e = conv(self.conv_in, cond_nhwc8, act=ACT_SILU)
         for blk in self.blocks:
             e = conv(blk, e, act=ACT_SILU) if blk.stride == 1 else blk(e, act=ACT_SILU)
-        return self.conv_out(e, residual=residual)  # sample + controlnet_cond (controlnet.py:817) fused
+        return self.conv_out(e)
 
 
 class _DownBlock(nn.Module):
@@ -139,6 +139,7 @@ class ControlNetModel(PretrainedMixin, nn.Module):
         if mid_block_type != "UNetMidBlock2DCrossAttn":
             raise NotImplementedError(mid_block_type)
         self.mid_block = _MidBlock(block_out_channels[-1], temb, norm_eps, heads, cross_attention_dim)
+        self._static_cond = None
 
     @property
     def dtype(self):
@@ -149,11 +150,21 @@ class ControlNetModel(PretrainedMixin, nn.Module):
         return next(self.parameters()).device
 
     @torch.no_grad()
+    def cache_static_cond(self, controlnet_cond: torch.Tensor):
+        """Computes controlnet_cond_embedding(controlnet_cond) once; forward() reuses it for this tensor object."""
+        c = controlnet_cond
+        if self.config.controlnet_conditioning_channel_order == "bgr":
+            c = torch.flip(c, dims=[1])
+        emb = self.controlnet_cond_embedding(to_channels_last_bf16(c, 8))
+        self._static_cond = (controlnet_cond, controlnet_cond._version, self.conv_in._key(), emb)
+
+    @torch.no_grad()
     def forward(self, sample, timestep, encoder_hidden_states, controlnet_cond, conditioning_scale: float = 1.0,
                 class_labels=None, timestep_cond=None, attention_mask=None, added_cond_kwargs=None,
                 cross_attention_kwargs=None, guess_mode: bool = False, return_dict: bool = True,
                 skip_conv_in: bool = False, skip_time_emb: bool = False):
         order = self.config.controlnet_conditioning_channel_order
+        cond_obj = controlnet_cond
         if order == "bgr":
             controlnet_cond = torch.flip(controlnet_cond, dims=[1])
         elif order != "rgb":
@@ -173,10 +184,16 @@ class ControlNetModel(PretrainedMixin, nn.Module):
         if skip_time_emb:
             temb_act = torch.zeros_like(temb_act)  # SiLU(0) == 0
         # 2. pre-process (controlnet.py:802-817)
-        x = self.conv_in(to_channels_last_bf16(sample, 8))
-        if skip_conv_in:
-            x = torch.zeros_like(x)
-        x = self.controlnet_cond_embedding(to_channels_last_bf16(controlnet_cond, 8), x)
+        # The conditioning embedding depends only on the control image (controlnet.py:94-104, :815), not on t or the
+        # latents: a loop registers the image once (cache_static_cond) and every later call with that very tensor
+        # object reuses the embedding.  sample = conv_in(sample) + embedding (controlnet.py:802-817): the add is fused
+        # into conv_in's epilogue (bf16 sum of two bf16 tensors, same rounding as the reference's `sample + cond`).
+        st = self._static_cond
+        if st is not None and st[0] is cond_obj and st[1] == cond_obj._version and st[2] == self.conv_in._key():
+            cond_emb = st[3]
+        else:
+            cond_emb = self.controlnet_cond_embedding(to_channels_last_bf16(controlnet_cond, 8))
+        x = cond_emb if skip_conv_in else self.conv_in(to_channels_last_bf16(sample, 8), residual=cond_emb)
         ctx = encoder_hidden_states.to(BF16).contiguous()
         # 3./4. down + mid
         res = [x]

@@ -1,13 +1,22 @@
 // Fused softmax(Q K^T * scale) V for the spatial self / cross attention of the adapter, the ControlNet and the
 // UNets.  tcgen05 MMAs with TMEM accumulators, TMA-fed 128B-swizzled shared memory, online softmax in registers.
 //
-// One CTA = 128 query rows of one (batch, head) and one 64-wide slice of the value head dim; 256 threads:
+// One CTA = 128 query rows of one (batch, head) and one 64-wide slice of the value head dim; 128 + 128 * NS threads
+// (NS = number of softmax warpgroups = column splits of a score row, 1 or 2):
 //   warpgroup 0: warp 0 = TMA producer (Q once, then K and V tiles of 128 keys through SEPARATE 2-stage rings:
 //                a K slot is free as soon as its QK^T retired, so K runs two tiles ahead of the softmax),
 //                warp 1 = MMA issuer + TMEM allocator.  S = Q K^T (M128 N128, K = 64*DQ) into TMEM cols [0,128);
 //                O += P V (M128 N64 K128, V consumed MN-major) ACCUMULATED in TMEM cols [128,192).  Warps 2-3 idle.
-//   warpgroup 1: softmax, one thread per query row.  Per KV tile the 128 scores of the row are read from TMEM ONCE
-//                (4 tcgen05.ld, one wait) and the S buffer is released immediately so the next tile's QK^T overlaps
+//   warpgroups 1..NS: softmax.  NS = 1: one thread per query row; NS = 2 (default for head dim 64, round 2): TWO
+//                threads per row -- warp w and warp w + 4 own the same 32 TMEM lanes and split the 128 key columns
+//                of the tile 64 / 64.  The row max is combined through a 1 KB shared-memory exchange and a 64-thread
+//                named barrier per warp pair; the row sum and the output columns stay split until the item's epilogue.
+//                Why: ncu (profiles/r2_ncu_attn4k_base.md) showed each softmax warp issuing only 24 % of the cycles,
+//                31 % lost to fixed-latency dependency stalls plus a tail of ~50 back-to-back MUFU.EX2 -- with two
+//                softmax warps per SM sub-partition nothing covers them.  Splitting rows doubles the warps per
+//                sub-partition (4) at half the registers each, same instruction count.
+//                Per KV tile the scores of the row (half) are read from TMEM ONCE
+//                (tcgen05.ld, one wait) and the S buffer is released immediately so the next tile's QK^T overlaps
 //                this tile's softmax.  The running max is "lazy": O (in TMEM) and the row sum are rescaled only when a
 //                row's max grew by more than 2^8 since the max in use (exact: softmax is shift invariant and exp2
 //                arguments stay <= 8), so the common path never touches O.
@@ -16,9 +25,9 @@
 //   * MUFU.EX2 (16 / clk / SM) is the scarcest pipe: a compile-time share of the exponentials (kPolyOf8 pairs out of
 //     8) is evaluated on the FMA pipe instead -- Cody-Waite split, cubic minimax 2^f on [-0.5, 0.5] (7.5e-5 relative,
 //     1/26 of a bf16 half-ulp of P), exponent spliced in with an integer add;
-//   * setmaxnreg moves registers from warpgroup 0 to the softmax warpgroup (208 each; warpgroup 0 keeps 48 -- with
-//     fewer the MMA issuer spills its descriptors and every tcgen05.mma issue costs hundreds of cycles) so the 128 scores of
-//     a row stay in registers without spills while two CTAs still share an SM;
+//   * setmaxnreg moves registers from warpgroup 0 to the softmax warpgroups (NS = 1: 208 each, NS = 2: 96 each;
+//     warpgroup 0 keeps 48 -- with fewer the MMA issuer spills its descriptors and every tcgen05.mma issue costs hundreds
+//     of cycles) so the scores of a row (half) stay in registers without spills while two CTAs still share an SM;
 //   * the producer / MMA warps back off with nanosleep while blocked so their polling does not steal issue slots.
 // With head dim 64 the CTA uses 113 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's softmax overlaps
 // the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3 (one CTA per SM).
@@ -30,7 +39,7 @@
 
 namespace ca {
 
-static constexpr int kAttnThreads = 256;
+static constexpr int kSplitDefault = 2;  // softmax warpgroups per CTA (column halves of a score row) for head dim 64
 static constexpr int kPolyDefault = 2;  // pairs out of every 8 whose exp2 runs on the FMA pipe instead of MUFU
 static constexpr int kTileQ = 128;
 static constexpr int kTileKV = 128;
@@ -41,7 +50,7 @@ template <int DQ>
 struct AttnCfg {
   static constexpr int kStages = 2;
   static constexpr uint32_t kQBytes = DQ * kChunkBytes;
-  static constexpr uint32_t kPBytes = 2 * kChunkBytes;
+  static constexpr uint32_t kPBytes = 2 * kChunkBytes;  // no longer holds P (tensor memory does): row max / row sum exchange
   static constexpr uint32_t kStageBytes = (DQ + 1) * kChunkBytes;  // K chunks + one V slice
   // data + 1024: the slack serves both the 1024-byte alignment of the swizzled tiles and the mbarriers.
   // For DQ == 1 this is 115712 B, i.e. exactly two CTAs per SM: 2 x (115712 + 1024 reserved) = 233472 = 228 KB.
@@ -90,8 +99,19 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
-template <int DQ, int POLY, bool PT>
-__global__ void __launch_bounds__(kAttnThreads, (DQ == 1) ? 2 : 1)
+// 64-thread named barrier of the warp pair (w, w + 4) that shares TMEM lane quarter q; immediate ids so that the kernel
+// reserves 5 hardware barriers, not all 16 (two CTAs share an SM)
+__device__ __forceinline__ void pair_bar_sync(int q) {
+  switch (q) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+template <int DQ, int POLY, int NS>
+__global__ void __launch_bounds__(128 + 128 * NS, (DQ == 1) ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   using Cfg = AttnCfg<DQ>;
@@ -101,8 +121,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   if (pad + Cfg::kDataBytes + 128 > Cfg::kSmemBytes) __trap();  // barriers would not fit behind the tiles
+  constexpr int kCols = kTileKV / NS;     // score columns per softmax thread
+  constexpr int kChunks = kCols / 32;     // 32-column TMEM loads per thread and tile
   uint8_t* smem_q = smem;
   uint8_t* smem_p = smem + Cfg::kQBytes;
+  [[maybe_unused]] float* xch_max = reinterpret_cast<float*>(smem_p);          // [2 tile parities][2 halves][128 rows]
+  [[maybe_unused]] float* xch_sum = reinterpret_cast<float*>(smem_p) + 512;    // [2 halves][128 rows]
   uint8_t* smem_kv = smem_p + Cfg::kPBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* q_full = bars + 0;
@@ -148,8 +172,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       mbar_init(&v_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
-    mbar_init(p_full, 4);
+    mbar_init(s_empty, 4 * NS);
+    mbar_init(p_full, 4 * NS);
     mbar_init(o_full, 1);
     fence_mbar_init();
   }
@@ -161,7 +185,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
   CA_PDL_WAIT();  // prologue (barriers, TMEM) done: from here on global memory of the previous kernel is consumed
-  [[maybe_unused]] const uint32_t tmem_p = tmem_base + 192;  // PT: bf16 P, two keys per 32-bit cell, 64 columns
+  const uint32_t tmem_p = tmem_base + 192;  // bf16 P (A operand of the PV TS MMA), two keys per 32-bit cell, 64 columns
 
   if (warp < 4) {
     if constexpr (DQ == 1) setmaxnreg_dec<48>();
@@ -207,7 +231,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V tile) is MN-major
       const uint32_t q_addr = smem_u32(smem_q);
-      [[maybe_unused]] const uint32_t p_addr = smem_u32(smem_p);
       TR_DECL(tr_kv_full);
       TR_DECL(tr_s_empty);
       TR_DECL(tr_p_full);
@@ -258,12 +281,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
-            if constexpr (PT) {
-              umma_bf16_ts(tmem_o, tmem_p + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // 16 keys = 8 TMEM cells
-            } else {
-              const uint64_t da = umma_smem_desc_sw128(p_addr + (k >> 2) * kChunkBytes + (k & 3) * 32, 16, 1024);
-              umma_bf16_ss(tmem_o, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // accumulate across KV tiles in TMEM
-            }
+            umma_bf16_ts(tmem_o, tmem_p + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);  // 16 keys = 8 TMEM cells
           }
           umma_commit(o_full);
           umma_commit(&v_empty[st]);
@@ -278,19 +296,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       TR_PUT(8, TR_NOW() - tr_start);
     }
   } else if (warp >= 4) {
-    // ===================== softmax / output: one thread per query row =====================
-    if constexpr (DQ == 1) setmaxnreg_inc<208>();
+    // ===================== softmax / output: NS threads per query row =====================
+    if constexpr (DQ == 1) setmaxnreg_inc<(NS == 1) ? 208 : 96>();
     // the two persistent CTAs of an SM start together; offset one of them by about half a KV tile so their MUFU-heavy
     // exp phases interleave instead of colliding (whichever way the hardware pairs block ids onto SMs)
     if (p.stagger_ns > 0 && gridDim.x > 148 && (((blockIdx.x / 148) ^ blockIdx.x) & 1)) __nanosleep(p.stagger_ns);
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int hf = (warp - 4) >> 2;         // column half (0 for NS == 1)
     const int r = q * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_col = static_cast<uint32_t>(hf * kCols);             // first score column of this thread
+    const uint32_t p_cell = static_cast<uint32_t>(hf * (kCols / 2));      // first packed-P cell (two keys per cell)
+    constexpr int kOCols = 64 / NS;                                        // output columns this thread rescales / writes
+    const uint32_t o_col = static_cast<uint32_t>(hf * kOCols);
     const float sl2 = p.scale_log2;
     float m_used = -INFINITY;  // the max (raw score units) the accumulated P / O / l are expressed against
-    float l_run = 0.f;
-    [[maybe_unused]] uint8_t* p_row = smem_p + r * 128;
-    [[maybe_unused]] const int sw = r & 7;
+    float l_run = 0.f;         // row sum over this thread's columns
     TR_DECL(tr_s_full);
     TR_DECL(tr_o_full);
     TR_DECL(tr_ld);
@@ -305,44 +326,52 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       TR_WAIT(tr_s_full, mbar_wait(s_full, g & 1));
       if (tr_me) TR_EVT(20);
       tc_fence_after();
-      uint32_t sv[4][32];
       // partial last KV tile: only the 32-column chunks that hold a valid key are processed (the P columns
-      // of the others are written as zeros); inside the boundary chunk invalid scores become -inf before the max, so the
-      // exp code below is the same as for a full tile
-      const int nch = MASK ? (kv_valid + 31) >> 5 : 4;
+      // of the others are written as zeros); inside the boundary chunk invalid scores become -inf, so the
+      // code below is the same as for a full tile
+      const int my_valid = MASK ? max(0, min(kCols, kv_valid - static_cast<int>(s_col))) : kCols;
+      const int nch = MASK ? (my_valid + 31) >> 5 : kChunks;
+      // ---- pass 1 over the scores (TMEM -> registers, transient): row max ----
+      // The scores are read from tensor memory TWICE (max pass, exp pass) instead of being held in registers across
+      // both: a tcgen05.ld of 32 columns costs a few issue cycles, while 64-128 live score registers per thread are what
+      // limits the number of softmax warps an SM can hold (the register file, not the MUFU pipe, is the scarce resource).
+      float m_tile;
+      {
+        uint32_t sv[kChunks][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_s + lane_sel + c * 32, sv[c]);
-      TR_WAIT(tr_ld, tmem_ld_wait());
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite the TMEM buffer
-      if (tr_me) TR_EVT(21);
-      // ---- row max ----
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        for (int c = 0; c < kChunks; ++c) tmem_ld_32x32(tmem_s + lane_sel + s_col + c * 32, sv[c]);
+        TR_WAIT(tr_ld, tmem_ld_wait());
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (MASK && c >= nch) continue;
-        if constexpr (MASK) {  // invalid scores of the boundary chunk become -inf, in place (exp2 -> 0)
-          const int lim = kv_valid - c * 32;
+        for (int c = 0; c < kChunks; ++c) {
+          if (MASK && c >= nch) continue;
+          const int lim = my_valid - c * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sv[c][i] = (i < lim) ? sv[c][i] : 0xff800000u;
+          for (int i = 0; i < 32; i += 2) {
+            const float a0 = (!MASK || i < lim) ? __uint_as_float(sv[c][i]) : -INFINITY;
+            const float a1 = (!MASK || i + 1 < lim) ? __uint_as_float(sv[c][i + 1]) : -INFINITY;
+            mx0 = fmaxf(mx0, a0);
+            mx1 = fmaxf(mx1, a1);
+          }
         }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sv[c][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sv[c][i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sv[c][i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(sv[c][i + 3]));
-        }
+        m_tile = fmaxf(mx0, mx1);
       }
-      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (tr_me) TR_EVT(21);
+      if constexpr (NS == 2) {
+        // combine with the thread that owns the other 64 columns of this row (warp +-4, same lane): buffers alternate
+        // with the tile parity, so a thread running ahead never overwrites a value its partner has not read yet
+        float* slot = xch_max + (g & 1) * 256;
+        slot[hf * 128 + r] = m_tile;
+        pair_bar_sync(q);
+        m_tile = fmaxf(m_tile, slot[(hf ^ 1) * 128 + r]);
+      }
       // ---- lazy rescale: only when this row's max exceeds the max in use by more than 2^8 ----
       bool waited_o = false;
       if (j == 0) {
         m_used = m_tile;
       } else {
         const bool need = (m_tile - m_used) * sl2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
+        if (__any_sync(0xffffffffu, need)) {  // both halves of a row take the same decision (same m_tile, m_used)
 #ifdef CA_TRACE
           ++tr_resc;
 #endif
@@ -353,34 +382,52 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (need) m_used = m_tile;
           l_run *= alpha;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < kOCols / 32; ++c) {
             uint32_t ov[32];
-            tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
+            tmem_ld_32x32(tmem_o + lane_sel + o_col + c * 32, ov);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st_32x32(tmem_o + lane_sel + c * 32, ov);
+            tmem_st_32x32(tmem_o + lane_sel + o_col + c * 32, ov);
           }
           tmem_st_wait();
         }
       }
-      // ---- p = exp2(s*sl2 - m_used*sl2) (<= 2^8), row sum, bf16 P ----
+      // P of tile j-1 must have been consumed by its PV MMA before it is overwritten
+      if (j > 0 && !waited_o) {
+        TR_WAIT(tr_o_full, mbar_wait(o_full, (g - 1) & 1));
+        tc_fence_after();
+      }
+      // ---- pass 2: p = exp2(s*sl2 - m_used*sl2) (<= 2^8), row sum, bf16 P, 32 columns at a time ----
       const float mneg = -m_used * sl2;
-      float rs0, rs1;
-      {
-        const uint64_t sl2_2 = pack_f32x2(sl2, sl2), mneg_2 = pack_f32x2(mneg, mneg);
-        uint64_t rs_a = pack_f32x2(0.f, 0.f), rs_b = rs_a;
+      const uint64_t sl2_2 = pack_f32x2(sl2, sl2), mneg_2 = pack_f32x2(mneg, mneg);
+      uint64_t rs = pack_f32x2(0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (MASK && c >= nch) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sv[c][i] = 0u;  // P = 0 for keys that do not exist
-            continue;
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t pw[16];
+        if (MASK && c >= nch) {
+          if (c == kChunks - 1) {  // the S buffer is released by the last chunk's turn even when that chunk is empty
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
           }
 #pragma unroll
+          for (int i = 0; i < 16; ++i) pw[i] = 0u;  // P = 0 for keys that do not exist
+        } else {
+          uint32_t sc[32];
+          tmem_ld_32x32(tmem_s + lane_sel + s_col + c * 32, sc);
+          tmem_ld_wait();
+          if (c == kChunks - 1) {  // every score of the tile has been read for the last time: the next QK^T may start
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty);
+          }
+          const int lim = my_valid - c * 32;
+#pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const uint64_t x =
-                fma_f32x2(pack_f32x2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sl2_2, mneg_2);
+            const float s0 = (!MASK || i < lim) ? __uint_as_float(sc[i]) : -INFINITY;
+            const float s1 = (!MASK || i + 1 < lim) ? __uint_as_float(sc[i + 1]) : -INFINITY;
+            const uint64_t x = fma_f32x2(pack_f32x2(s0, s1), sl2_2, mneg_2);
             float x0, x1, p0, p1;
             unpack_f32x2(x, x0, x1);
             if (pair_uses_poly<POLY>(i >> 1)) {
@@ -389,47 +436,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
             }
-            if ((i >> 1) & 1) rs_b = add_f32x2(rs_b, pack_f32x2(p0, p1));
-            else rs_a = add_f32x2(rs_a, pack_f32x2(p0, p1));
-            sv[c][i >> 1] = pack_bf16x2(p0, p1);  // packed P overwrites the already consumed scores in place
+            rs = add_f32x2(rs, pack_f32x2(p0, p1));
+            pw[i >> 1] = pack_bf16x2(p0, p1);
           }
         }
-        unpack_f32x2(add_f32x2(rs_a, rs_b), rs0, rs1);
-      }
-      l_run += rs0 + rs1;
-      if (tr_me) TR_EVT(22);
-      // P of tile j-1 must have been consumed by its PV MMA before it is overwritten
-      if (j > 0 && !waited_o) {
-        TR_WAIT(tr_o_full, mbar_wait(o_full, (g - 1) & 1));
-        tc_fence_after();
-      }
-      if constexpr (PT) {
         // P goes to tensor memory (the PV MMA reads its A operand from there): no shared-memory stores, no proxy fence
-        uint32_t pw[32];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            pw[i] = sv[2 * hh][i];
-            pw[16 + i] = sv[2 * hh + 1][i];
-          }
-          tmem_st_32x32(tmem_p + lane_sel + hh * 32, pw);
-        }
-        tmem_st_wait();
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint8_t* chunk = p_row + (c >> 1) * kChunkBytes;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int unit = (c & 1) * 4 + u;  // 16-byte unit inside the 128-byte row
-            *reinterpret_cast<uint4*>(chunk + ((unit ^ sw) << 4)) =
-                make_uint4(sv[c][u * 4], sv[c][u * 4 + 1], sv[c][u * 4 + 2], sv[c][u * 4 + 3]);
-          }
-        }
-        fence_proxy_async_smem();  // P stores -> visible to the tensor core (async proxy)
+        tmem_st_32x16(tmem_p + lane_sel + p_cell + c * 16, pw);
       }
-      tc_fence_before();         // orders the tcgen05.st of a rescale before the MMA that follows the barrier
+      {
+        float rs0, rs1;
+        unpack_f32x2(rs, rs0, rs1);
+        l_run += rs0 + rs1;
+      }
+      if (tr_me) TR_EVT(22);
+      tmem_st_wait();
+      tc_fence_before();         // orders the tcgen05.st (P, and O of a rescale) before the MMA that follows the barrier
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       if (tr_me) TR_EVT(23);
@@ -446,17 +467,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         else tile_step(std::true_type{}, j, g, kv_valid);
       }
       // epilogue: O / l (the next item's first QK^T and its loads are already in flight)
+      float l_row = l_run;
+      if constexpr (NS == 2) {
+        // the row sum is split like the columns; single buffer: at least one max exchange (a barrier of this warp pair)
+        // separates two epilogues, so the partner has read the previous item's value before it is overwritten
+        xch_sum[hf * 128 + r] = l_run;
+        pair_bar_sync(q);
+        l_row += xch_sum[(hf ^ 1) * 128 + r];
+      }
       TR_WAIT(tr_epi_o, mbar_wait(o_full, (g - 1) & 1));
       if (tr_me) TR_EVT(24);
       tc_fence_after();
-      const float inv_l = 1.0f / l_run;
+      const float inv_l = 1.0f / l_row;
       const int row = q0 + r;
       __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_batch_stride +
-                            static_cast<long long>(row) * p.out_row_stride + h * dpad + vs * 64;
+                            static_cast<long long>(row) * p.out_row_stride + h * dpad + vs * 64 + o_col;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < kOCols / 32; ++c) {
         uint32_t ov[32];
-        tmem_ld_32x32(tmem_o + lane_sel + c * 32, ov);
+        tmem_ld_32x32(tmem_o + lane_sel + o_col + c * 32, ov);
         tmem_ld_wait();
         if (row < p.lq) {
 #pragma unroll
@@ -489,16 +518,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-template <int DQ, int POLY, bool PT>
+template <int DQ, int POLY, int NS>
 static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream) {
   using Cfg = AttnCfg<DQ>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::kSmemBytes));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, PT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, NS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -516,28 +545,28 @@ static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const C
   // developer knobs: CA_ATTN_GRID=items launches one CTA per work item (hardware block scheduler, dynamic balance)
   static const bool per_item = getenv("CA_ATTN_GRID") && getenv("CA_ATTN_GRID")[0] == 'i';
   const int grid = static_cast<int>((items < resident || per_item) ? items : resident);
-  auto kern = attention_kernel<DQ, POLY, PT>;
-  CA_KERNEL_LAUNCH(kern, grid, kAttnThreads, Cfg::kSmemBytes, stream, q, k, v, p);
+  auto kern = attention_kernel<DQ, POLY, NS>;
+  CA_KERNEL_LAUNCH(kern, grid, 128 + 128 * NS, Cfg::kSmemBytes, stream, q, k, v, p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream) {
+  // developer knobs: CA_ATTN_SPLIT = softmax warpgroups per CTA (1 = one thread per row as in round 1, 2 = two);
+  // CA_ATTN_POLY = share of exponentials moved off the MUFU pipe (eighths)
+  static const int split = getenv("CA_ATTN_SPLIT") ? atoi(getenv("CA_ATTN_SPLIT")) : kSplitDefault;
+  static const int poly = getenv("CA_ATTN_POLY") ? atoi(getenv("CA_ATTN_POLY")) : kPolyDefault;
   switch (p.dqk_chunks) {
-    case 1: {
-      // developer knobs: CA_ATTN_POLY = share of exponentials moved off the MUFU pipe (eighths);
-      // CA_ATTN_PSMEM=1 stages P through shared memory (SS MMA) instead of tensor memory (TS MMA)
-      static const int poly = getenv("CA_ATTN_POLY") ? atoi(getenv("CA_ATTN_POLY")) : kPolyDefault;
-      static const bool psmem = getenv("CA_ATTN_PSMEM") != nullptr;
-      if (psmem) return launch_dq<1, kPolyDefault, false>(q, k, v, p, stream);
+    case 1:
+      if (split == 1) return launch_dq<1, kPolyDefault, 1>(q, k, v, p, stream);
       switch (poly) {
-        case 0: return launch_dq<1, 0, true>(q, k, v, p, stream);
-        case 3: return launch_dq<1, 3, true>(q, k, v, p, stream);
-        default: return launch_dq<1, kPolyDefault, true>(q, k, v, p, stream);
+        case 0: return launch_dq<1, 0, 2>(q, k, v, p, stream);
+        case 3: return launch_dq<1, 3, 2>(q, k, v, p, stream);
+        case 4: return launch_dq<1, 4, 2>(q, k, v, p, stream);
+        default: return launch_dq<1, kPolyDefault, 2>(q, k, v, p, stream);
       }
-    }
-    case 2: return launch_dq<2, kPolyDefault, true>(q, k, v, p, stream);
-    case 3: return launch_dq<3, kPolyDefault, true>(q, k, v, p, stream);
+    case 2: return split == 1 ? launch_dq<2, kPolyDefault, 1>(q, k, v, p, stream) : launch_dq<2, kPolyDefault, 2>(q, k, v, p, stream);
+    case 3: return split == 1 ? launch_dq<3, kPolyDefault, 1>(q, k, v, p, stream) : launch_dq<3, kPolyDefault, 2>(q, k, v, p, stream);
     default: return cudaErrorInvalidValue;
   }
 }

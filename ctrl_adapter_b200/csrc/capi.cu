@@ -131,9 +131,11 @@ int ca_gemm(const ca_gemm_desc* d, void* cuda_stream) {
     else if (d->w_rows <= 128) bn = 128;
     else bn = 256;
   }
-  // EXPERIMENT (off unless CA_GEMM_BN320=1): 256 x 320 pair tiles where 160-wide ones are used today
-  // (csrc/gemm_conv_wide.cu); only for the bias / bias+residual epilogues, CTA pairs, bf16 output
-  static const bool wide_ok = getenv("CA_GEMM_BN320") != nullptr && getenv("CA_GEMM_1CTA") == nullptr;
+  // 256 x 320 pair tiles (csrc/gemm_conv_wide.cu) where the N = 320 / 640 / 960 / 1920 GEMMs would otherwise use 160-wide
+  // ones (L2-feed bound); only for the bias / bias+residual epilogues, CTA pairs, bf16 output.  Default since round 2
+  // (kernel checks green on hardware, 181.8 -> 179.7 ms / SDXL step); CA_GEMM_BN320=0 restores the 160-wide tiles.
+  static const bool wide_ok = !(getenv("CA_GEMM_BN320") && getenv("CA_GEMM_BN320")[0] == '0') &&
+                              getenv("CA_GEMM_1CTA") == nullptr;
   if (wide_ok && d->bn == 0 && bn == 160 && d->w_rows % 320 == 0 && d->act == CA_ACT_NONE && !d->out_fp32 &&
       d->out_scale == 1.0f && d->blend_src == nullptr && (d->rowvec == nullptr || d->residual == nullptr) &&
       reinterpret_cast<uintptr_t>(d->bias) % 16 == 0)

@@ -224,6 +224,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// registers -> TMEM, 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 32 lanes x 16 columns
@@ -342,14 +351,15 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
 }  // namespace ca
 
 // ---------------------------------------------------------------------------------------------------------------
-// Programmatic dependent launch (experiment, compiled in with -DCA_PDL only; see scripts/build_variants.py).
+// Programmatic dependent launch (default since round 2: 181.8 -> 175.8 ms / SDXL step, profiles/r2_experiments.md;
+// -DCA_NO_PDL builds without it, see scripts/build_variants.py).
 // With ~1500 launches per step, every kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) and the
-// launch latency itself sit between the tail of one kernel and the first useful cycle of the next.  Under CA_PDL each
+// launch latency itself sit between the tail of one kernel and the first useful cycle of the next.  With PDL each
 // kernel (a) tells the scheduler right away that its dependents may be launched as SMs free up and (b) waits for the
 // previous grid's completion only after its own prologue, before the first global-memory access.  Without the launch
-// attribute both instructions are no-ops, and without -DCA_PDL neither is emitted.
+// attribute both instructions are no-ops, and with -DCA_NO_PDL neither is emitted.
 // ---------------------------------------------------------------------------------------------------------------
-#ifdef CA_PDL
+#ifndef CA_NO_PDL
 #define CA_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;")
 #define CA_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 namespace ca {

@@ -248,7 +248,10 @@ cudaError_t launch_router_weights(const float* logits, const unsigned char* mask
 }
 
 // y = sum_e w[e] * x_e with the reference's bf16 rounding after each multiply and add
-__global__ void router_merge_kernel(const __nv_bfloat16* const* __restrict__ xs, const float* __restrict__ w,
+struct RouterSources {  // expert tensors by value: nothing to stage on the device, so the launch is graph-capturable
+  const __nv_bfloat16* p[kMaxRouterExperts];
+};
+__global__ void router_merge_kernel(const __grid_constant__ RouterSources xs, const float* __restrict__ w,
                                     int nactive, long long nvec, uint4* __restrict__ y) {
   CA_PDL_TRIGGER();
   CA_PDL_WAIT();
@@ -259,7 +262,7 @@ __global__ void router_merge_kernel(const __nv_bfloat16* const* __restrict__ xs,
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     for (int k = 0; k < nactive; ++k) {
       const float wk = round_bf16(w[k]);
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xs[k]) + i);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xs.p[k]) + i);
       const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&u);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -271,10 +274,12 @@ __global__ void router_merge_kernel(const __nv_bfloat16* const* __restrict__ xs,
                       pack_bf16x2(acc[6], acc[7]));
   }
 }
-cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, int nactive, long long n,
+cudaError_t launch_router_merge(const __nv_bfloat16* const* xs_host, const float* w, int nactive, long long n,
                                 __nv_bfloat16* y, cudaStream_t stream) {
-  if (n & 7) return cudaErrorInvalidValue;
-  CA_KERNEL_LAUNCH(router_merge_kernel, blocks_for(n / 8, 256), 256, 0, stream, xs, w, nactive, n / 8, reinterpret_cast<uint4*>(y));
+  if ((n & 7) || nactive < 1 || nactive > kMaxRouterExperts) return cudaErrorInvalidValue;
+  RouterSources src{};
+  for (int k = 0; k < nactive; ++k) src.p[k] = xs_host[k];
+  CA_KERNEL_LAUNCH(router_merge_kernel, blocks_for(n / 8, 256), 256, 0, stream, src, w, nactive, n / 8, reinterpret_cast<uint4*>(y));
   return cudaGetLastError();
 }
 

@@ -335,11 +335,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
             // fp32 bias rows: value columns (and the matching gate rows for GEGLU); uniform addresses -> broadcast
             const float4* bias_a = reinterpret_cast<const float4*>(p.bias + (kGeglu ? tn * BN + c0 : col0 + c0));
             [[maybe_unused]] const float4* bias_g = reinterpret_cast<const float4*>(p.bias + tn * BN + BN / 2 + c0);
-#ifdef CA_EXP_EPI
-            // EXPERIMENT (-DCA_EXP_EPI): issue every bias load of this 32-column slice BEFORE waiting for the TMEM load.
-            // In the default code the loads sit inside the per-8-column loop behind its early exit, so each group
-            // pays an exposed L1/L2 round trip (4 x ~0.3-0.5k cycles per slice: most of the epilogue's latency, which is
-            // what bounds the small-K GEMMs and the un-overlapped epilogue of every launch's last tile).
+            // every bias load of this 32-column slice is issued BEFORE waiting for the TMEM load: inside the per-8-column
+            // loop (behind its early exit) each group paid an exposed L1/L2 round trip, most of the epilogue's latency,
+            // which bounds the small-K GEMMs and the un-overlapped epilogue of every launch's last tile
+            // (round 2 A/B: 181.8 -> 174.9 ms / SDXL step, profiles/r2_experiments.md)
             float4 bq[8];
             [[maybe_unused]] float4 bqg[kGeglu ? 8 : 1];
             if (has_bias) {
@@ -355,7 +354,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
                 }
               }
             }
-#endif
             TR_WAIT(tr_tmem, tmem_ld_wait());
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
@@ -364,11 +362,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(va[j8 * 8 + e]);
               if (has_bias) {
-#ifdef CA_EXP_EPI
                 const float4 b0 = bq[j8 * 2], b1 = bq[j8 * 2 + 1];
-#else
-                const float4 b0 = __ldg(bias_a + j8 * 2), b1 = __ldg(bias_a + j8 * 2 + 1);
-#endif
                 x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
                 x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
               }
@@ -380,11 +374,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
 #pragma unroll
                 for (int e = 0; e < 8; ++e) g[e] = __uint_as_float(vg[j8 * 8 + e]);
                 if (has_bias) {
-#ifdef CA_EXP_EPI
                   const float4 b0 = bqg[j8 * 2], b1 = bqg[j8 * 2 + 1];
-#else
-                  const float4 b0 = __ldg(bias_g + j8 * 2), b1 = __ldg(bias_g + j8 * 2 + 1);
-#endif
                   g[0] += b0.x; g[1] += b0.y; g[2] += b0.z; g[3] += b0.w;
                   g[4] += b1.x; g[5] += b1.y; g[6] += b1.z; g[7] += b1.w;
                 }
@@ -672,7 +662,7 @@ static cudaError_t launch_cfg(const CUtensorMap& a0, const CUtensorMap& a1, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-#ifdef CA_PDL
+#ifndef CA_NO_PDL
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.numAttrs = 2;

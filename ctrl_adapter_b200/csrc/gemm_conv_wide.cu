@@ -1,5 +1,6 @@
-// EXPERIMENT (not dispatched unless CA_GEMM_BN320=1; no hardware run yet): the multi-tap tcgen05 GEMM of
-// gemm_conv_kernel.cuh with 256 x 320 CTA-pair tiles for the N = 320 / 640 / 960 / 1920 convolutions and linears.
+// The multi-tap tcgen05 GEMM of gemm_conv_kernel.cuh with 256 x 320 CTA-pair tiles for the N = 320 / 640 / 960 / 1920
+// convolutions and linears (default dispatch since round 2: kernel checks green on hardware, profiles/r2_experiments.md;
+// CA_GEMM_BN320=0 falls back to the 160-wide tiles).
 //
 // Why: the operand feed of the GEMM is bound by L2 -> SM bandwidth (~6.3 KB / clk chip-wide, profiles/README.md).  With
 // BN = 160 tiles a k-block moves 16 KB (A) + 10 KB (B) per CTA for 128 x 160 x 64 MACs and the tensor pipe tops out
@@ -312,7 +313,7 @@ static cudaError_t launch_wide(const CUtensorMap& a0, const CUtensorMap& a1, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-#ifdef CA_PDL
+#ifndef CA_NO_PDL
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.numAttrs = 2;

@@ -83,7 +83,8 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* x, int n, int h, int w, int c
                               cudaStream_t stream);
 cudaError_t launch_router_weights(const float* logits, const unsigned char* mask, int nrouters, int nexperts,
                                   float* weights, cudaStream_t stream);
-cudaError_t launch_router_merge(const __nv_bfloat16* const* xs, const float* w, int nactive, long long n,
+static constexpr int kMaxRouterExperts = 8;
+cudaError_t launch_router_merge(const __nv_bfloat16* const* xs_host, const float* w, int nactive, long long n,
                                 __nv_bfloat16* y, cudaStream_t stream);
 cudaError_t launch_cfg_euler_v(const __nv_bfloat16* eps_uncond, const __nv_bfloat16* eps_text, const float* latents_in,
                                long long n, const float* guidance, int frames, long long frame_elems,

@@ -277,7 +277,7 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
                 d.tap_off[t][0], d.tap_off[t][1] = dx - 1, dy - 1
         d.out_dims[0], d.out_dims[1], d.out_dims[2], d.out_dims[3] = wo, ho, n, 1
         os_ = (cout, wo * cout, ho * wo * cout, 0)
-        rvs = (0, 0, cout if (rowvec is not None and rowvec.shape[0] > 1) else 0, 0)
+        rvs = (0, 0, rowvec.stride(0) if (rowvec is not None and rowvec.shape[0] > 1) else 0, 0)
     else:
         assert ksize == 3 and x2 is None and h % 2 == 0 and w_ % 2 == 0
         # parity view: channel axis [x parity][C], row dims (x/2, y parity, y/2, n)
@@ -294,7 +294,7 @@ def conv2d(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor]
             d.tap_c_off[t] = px * c
         d.out_dims[0], d.out_dims[1], d.out_dims[2], d.out_dims[3] = wo, 1, ho, n
         os_ = (cout, 0, wo * cout, ho * wo * cout)
-        rvs = (0, 0, 0, cout if (rowvec is not None and rowvec.shape[0] > 1) else 0)
+        rvs = (0, 0, 0, rowvec.stride(0) if (rowvec is not None and rowvec.shape[0] > 1) else 0)
     for i in range(4):
         d.out_strides[i] = os_[i]
     d.w = w_packed.data_ptr(); d.w_rows = cout; d.w_k_per_tap = kpt
@@ -341,7 +341,7 @@ def temporal_conv(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.
     d.w = w_packed.data_ptr(); d.w_rows = cout; d.w_k_per_tap = w_packed.shape[1] // 3
     d.out = out.data_ptr(); d.n_out = cout
     _fill_epilogue(d, bias=bias, act=ACT_NONE, out_scale=1.0, rowvec=rowvec,
-                   rowvec_strides=((0, cout, frames * cout, 0) if rowvec.shape[0] > 1 else (0, 0, 0, 0)) if rowvec is not None else None,
+                   rowvec_strides=((0, rowvec.stride(0), frames * rowvec.stride(0), 0) if rowvec.shape[0] > 1 else (0, 0, 0, 0)) if rowvec is not None else None,
                    residual=residual,
                    blend_src=blend_src, res_strides=os_ if (residual is not None or blend_src is not None) else None,
                    blend_alpha=blend_alpha)
@@ -519,16 +519,17 @@ def router_weights(logits: torch.Tensor, mask: Optional[torch.Tensor]):
     return out
 
 
-def router_merge(xs: Sequence[torch.Tensor], w: torch.Tensor, ptr_table: Optional[torch.Tensor] = None):
+def router_merge(xs: Sequence[torch.Tensor], w: torch.Tensor):
     """y = sum_k w[k] * xs[k] (bf16 rounding after every multiply / add as in the reference loop)."""
     for x in xs:
         _req(x)
     _req(w, torch.float32)
-    if ptr_table is None:
-        ptr_table = torch.tensor([x.data_ptr() for x in xs], dtype=torch.int64).to(xs[0].device)
+    if not 1 <= len(xs) <= 8:
+        raise ValueError("router_merge takes 1..8 expert tensors")
+    ptrs = (C.c_void_p * len(xs))(*[x.data_ptr() for x in xs])  # host array: pointers are passed to the kernel by value
     y = torch.empty_like(xs[0])
-    _launch("router_merge", 0.0, 2.0 * (len(xs) + 1) * xs[0].numel(), "ca_router_merge", ptr_table.data_ptr(), w.data_ptr(), len(xs), xs[0].numel(), y.data_ptr(),
-                                      _stream())
+    _launch("router_merge", 0.0, 2.0 * (len(xs) + 1) * xs[0].numel(), "ca_router_merge", ptrs, w.data_ptr(), len(xs),
+            xs[0].numel(), y.data_ptr(), _stream())
     return y
 
 

@@ -3,8 +3,9 @@ on the B200 modules:  [pool] -> ControlNet -> Ctrl-Adapter -> SDXL UNet (+ resid
 
 Everything outside the loop (prompt / image encoding, VAE) is out of scope; the loop takes the
 already-encoded conditioning tensors.  ``step()`` is the plain public-API path (module ``forward`` calls);
-``capture()`` records the same body once into a CUDA graph that is replayed for every timestep -- the per-step
-scalars (t, sigma, ...) live in a device row that is refreshed by a 16-byte device-to-device copy.
+``capture()`` records the same body into a CUDA graph that is replayed for every timestep (one graph per distinct
+conditioning scale, see loop_base.py) -- the per-step scalars (t, sigma, ...) live in a device row that is refreshed
+by a 16-byte device-to-device copy.
 """
 from __future__ import annotations
 
@@ -14,28 +15,31 @@ import torch
 
 from . import ops
 from .adapter import as_nchw, to_channels_last_bf16
+from .layers import cache_static_context
+from .loop_base import DenoiseLoopBase
 from .schedulers import EulerDiscreteSchedule
 
 BF16 = torch.bfloat16
 
 
-class SDXLControlNetAdapterLoop:
+class SDXLControlNetAdapterLoop(DenoiseLoopBase):
     def __init__(self, controlnet, adapter, unet, *, num_inference_steps: int = 50, guidance_scale: float = 5.0,
-                 controlnet_conditioning_scale: float = 1.0, use_size_512: bool = True):
+                 controlnet_conditioning_scale: float = 1.0, use_size_512: bool = True,
+                 control_guidance_start: float = 0.0, control_guidance_end: float = 1.0):
         self.controlnet, self.adapter, self.unet = controlnet, adapter, unet
         self.guidance_scale = float(guidance_scale)
         self.cond_scale = float(controlnet_conditioning_scale)
         self.use_size_512 = use_size_512
         self.schedule = EulerDiscreteSchedule(num_inference_steps)
         self.num_inference_steps = num_inference_steps
-        self._graph = None
+        self._init_control(controlnet_conditioning_scale, control_guidance_start, control_guidance_end, 1)
 
     # ------------------------------------------------------------------------------------------
     def prepare(self, latents: torch.Tensor, prompt_embeds: torch.Tensor, add_text_embeds: torch.Tensor,
                 add_time_ids: torch.Tensor, controlnet_prompt_embeds: torch.Tensor, control_images: torch.Tensor):
         """latents [B,4,h,w] (unit-variance noise, scaled here by init_noise_sigma as prepare_latents does);
         prompt_embeds [2B,77,2048] (negative first), add_text_embeds [2B,1280], add_time_ids [2B,6],
-        controlnet_prompt_embeds [2B,77,768], control_images [2B,3,512,512] in [0,1]."""
+        controlnet_prompt_embeds [2B,77,768], control_images [2B,3,H,W] in [0,1]."""
         dev = latents.device
         self.batch = latents.shape[0]
         self.latents = (latents.float() * self.schedule.init_noise_sigma).to(BF16).float().contiguous()
@@ -49,69 +53,48 @@ class SDXLControlNetAdapterLoop:
         self.added = dict(text_embeds=add_text_embeds.to(BF16).contiguous(),
                           time_ids=add_time_ids.float().contiguous())
         self.cn_embeds = controlnet_prompt_embeds.to(BF16).contiguous()
-        self.images = control_images.to(BF16).contiguous()
-        self._graph = None
+        images = control_images.to(BF16).contiguous()
+        h, w = latents.shape[-2:]
+        if (h, w) != (64, 64) and self.use_size_512 and tuple(images.shape[-2:]) != (512, 512):
+            # F.adaptive_avg_pool2d(images, (512, 512)) of the loop body (:1306-1312): step-invariant, done once here
+            if images.shape[-2] % 512 or images.shape[-1] % 512:
+                raise NotImplementedError("control images must be 512x512 or an integer multiple (adaptive pool windows)")
+            images = as_nchw(ops.avgpool(to_channels_last_bf16(images, 8), 512, 512))[:, :3].contiguous()
+        self.images = images
+        # step-invariant work, hoisted (exact: same kernels on the same operands, run once instead of every step):
+        # cross-attention K/V of the constant prompt embeddings, the ControlNet's conditioning-image embedding
+        cache_static_context(self.unet, self.prompt_embeds)
+        cache_static_context(self.adapter, self.prompt_embeds)
+        cache_static_context(self.controlnet, self.cn_embeds)
+        self.controlnet.cache_static_cond(self.images)
+        self._graphs = {}
         self.step_index = 0
 
+    def _state(self):
+        return [self.latents, self.model_in, self.row]
+
+    def _load_step(self, i):
+        self.row.copy_(self.table[i])
+
     # ------------------------------------------------------------------------------------------
-    def _body(self):
+    def _body(self, scale):
         b = self.batch
         t = self.row[0:1]
         lat2 = torch.cat([self.model_in, self.model_in], dim=0)  # CFG duplication (tiny latent-sized copy)
-        h, w = lat2.shape[-2:]
-        ctrl_in = lat2
-        if (h, w) != (64, 64) and self.use_size_512:  # pipeline :1306-1312; the image pool to 512^2 is an identity
-            ctrl_in = as_nchw(ops.avgpool(to_channels_last_bf16(lat2, 8), 64, 64))[:, :4]
-        down, mid = self.controlnet(ctrl_in, t, encoder_hidden_states=self.cn_embeds, controlnet_cond=self.images,
-                                    conditioning_scale=self.cond_scale, guess_mode=False, return_dict=False)
-        down_a, mid_a = self.adapter(down, sparsity_masking=None, num_frames=1, timestep=t,
-                                     encoder_hidden_states=self.prompt_embeds)
-        residuals = None if self.cond_scale == 0 else down_a
+        residuals = None
+        if scale != 0:
+            # with cond_scale == 0 the reference still runs ControlNet + adapter but discards their output (:1346, and
+            # mid_block_additional_residual is the constant 0): skipping the two modules is exact
+            h, w = lat2.shape[-2:]
+            ctrl_in = lat2
+            if (h, w) != (64, 64) and self.use_size_512:  # pipeline :1306-1312
+                ctrl_in = as_nchw(ops.avgpool(to_channels_last_bf16(lat2, 8), 64, 64))[:, :4]
+            down, mid = self.controlnet(ctrl_in, t, encoder_hidden_states=self.cn_embeds, controlnet_cond=self.images,
+                                        conditioning_scale=scale, guess_mode=False, return_dict=False)
+            residuals, _ = self.adapter(down, sparsity_masking=None, num_frames=1, timestep=t,
+                                        encoder_hidden_states=self.prompt_embeds)
         eps = self.unet(lat2, t, encoder_hidden_states=self.prompt_embeds, added_cond_kwargs=self.added,
                         down_block_additional_residuals=residuals, mid_block_additional_residual=0,
                         return_dict=False)[0]
         ops.cfg_euler(eps[:b], eps[b:], self.latents, self.guidance_scale, self.row, latents_out=self.latents,
                       model_in_next=self.model_in)
-
-    @torch.no_grad()
-    def step(self, i: Optional[int] = None):
-        """One denoising iteration through the modules' public forward()s (eager launches)."""
-        i = self.step_index if i is None else i
-        self.row.copy_(self.table[i])
-        self._body()
-        self.step_index = i + 1
-        return self.latents
-
-    @torch.no_grad()
-    def capture(self, warmup: int = 2):
-        """Record the step body into a CUDA graph (after `warmup` eager runs that pack weights and set kernel
-        attributes).  State (latents, model_in, row) is restored afterwards."""
-        saved = (self.latents.clone(), self.model_in.clone(), self.row.clone())
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._body()
-        torch.cuda.current_stream().wait_stream(s)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._body()
-        self._graph = g
-        self.latents.copy_(saved[0]); self.model_in.copy_(saved[1]); self.row.copy_(saved[2])
-        return g
-
-    @torch.no_grad()
-    def step_graph(self, i: Optional[int] = None):
-        if self._graph is None:
-            self.capture()
-        i = self.step_index if i is None else i
-        self.row.copy_(self.table[i])
-        self._graph.replay()
-        self.step_index = i + 1
-        return self.latents
-
-    @torch.no_grad()
-    def run(self, use_graph: bool = True):
-        for i in range(self.num_inference_steps):
-            (self.step_graph if use_graph else self.step)(i)
-        return self.latents

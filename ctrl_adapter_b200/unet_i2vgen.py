@@ -19,7 +19,7 @@ from torch import nn
 from . import ops
 from .persistence import PretrainedMixin
 from .adapter import _ConfigDict, timestep_vector, to_channels_last_bf16
-from .layers import (BF16, Attention, BasicTransformerBlock, Conv2d, FeedForward, Linear, Norm, Packable, ResnetBlock2D,
+from .layers import (cache_static_context, BF16, Attention, BasicTransformerBlock, Conv2d, FeedForward, Linear, Norm, Packable, ResnetBlock2D,
                      TemporalConv, TimestepEmbedding, Transformer2DModel)
 from .ops import ACT_SILU
 
@@ -276,6 +276,8 @@ class I2VGenXLUNet(PretrainedMixin, nn.Module):
                                                                            encoder_hidden_states))
         if self._cond_cache is None or self._cond_cache[0] != key:
             self._cond_cache = (key, self.prepare_conditioning(fps, image_latents, image_embeddings, encoder_hidden_states))
+            # the assembled context is as step-invariant as its inputs: project every cross attention's K/V once
+            cache_static_context(self, self._cond_cache[1]["ctx"])
         return self._cond_cache[1]
 
     @torch.no_grad()

@@ -165,7 +165,8 @@ int ca_upsample2x(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, voi
 int ca_router_weights(const float* logits, const uint8_t* mask, int32_t nrouters, int32_t nexperts, float* weights,
                       void* cuda_stream);
 /* Weighted merge of expert residuals (i2vgen_xl pipeline :1001-1022): y = sum_e w[e] * xs[e], bf16 rounding
- * after each multiply and each add as in the reference loop.  xs: device array of nactive pointers. */
+ * after each multiply and each add as in the reference loop.  xs: HOST array of nactive (<= 8) device pointers; they
+ * travel to the kernel by value, so the call is CUDA-graph capturable. */
 int ca_router_merge(const void* const* xs, const float* w, int32_t nactive, int64_t n, void* y, void* cuda_stream);
 
 /* Classifier-free guidance + scheduler update in one pass (latent-sized, HBM-bound).

@@ -10,6 +10,7 @@ import math
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 
 class DDIMScheduler:
@@ -57,7 +58,7 @@ class DDIMScheduler:
 @torch.no_grad()
 def i2vgen_step(controlnet, adapter, unet, scheduler, i, latents, prompt_embeds, image_latents, image_embeddings, fps,
                 controlnet_prompt_embeds, images, router=None, masks=None, guidance_scale=9.0, cond_scale=1.0,
-                sparse_frames=None):
+                sparse_frames=None, use_size_512=True):
     """latents (B,4,F,h,w).  One iteration of :902-1115.  sparse_frames: key-frame indices in [0, F) (:1024-1033,
     :1053-1073); the reference supports one clip with its CFG pair (index s of the conditional half is s + F), restated
     here for 2B clips as b*F + s."""
@@ -66,7 +67,11 @@ def i2vgen_step(controlnet, adapter, unet, scheduler, i, latents, prompt_embeds,
     latent_model_input = scheduler.scale_model_input(torch.cat([latents] * 2), t)                  # :904-905
     control_in = latent_model_input.permute(0, 2, 1, 3, 4).reshape(2 * b * f, c, h, w)             # :931
     multi = isinstance(images, (list, tuple))
-    scale = [cond_scale] * len(images) if multi else cond_scale
+    scale = list(cond_scale) if isinstance(cond_scale, (list, tuple)) else ([cond_scale] * len(images) if multi else cond_scale)
+    if (h, w) != (64, 64) and use_size_512:                                                         # :941-947
+        control_in = F.adaptive_avg_pool2d(control_in, (64, 64))
+        images = ([F.adaptive_avg_pool2d(im, (512, 512)) for im in images] if multi
+                  else F.adaptive_avg_pool2d(images, (512, 512)))
     down, mid = controlnet(control_in, t, encoder_hidden_states=controlnet_prompt_embeds, controlnet_cond=images,
                            conditioning_scale=scale, guess_mode=False, return_dict=False)          # :957-968
     if router is not None:                                                                          # :972-1022

@@ -1,12 +1,10 @@
 """Developer tool: builds experimental variants of the library next to the default one (selected at run time with
 CA_B200_LIB=<path>, see ctrl-adapter_b200/_lib.py).  Runs on the CPU box (nvcc cross-compiles).
 
-  python scripts/build_variants.py pdl      -> ctrl-adapter_b200/libctrl_adapter_b200_pdl.so    (-DCA_PDL)
-  python scripts/build_variants.py trace    -> ctrl-adapter_b200/libctrl_adapter_b200_trace.so  (-DCA_TRACE)
-  python scripts/build_variants.py epi      -> ..._epi.so  (-DCA_EXP_EPI: GEMM epilogue bias loads hoisted ahead of the TMEM wait)
-  python scripts/build_variants.py all      -> ..._all.so  (-DCA_PDL -DCA_EXP_EPI)
+  python scripts/build_variants.py nopdl    -> ctrl_adapter_b200/libctrl_adapter_b200_nopdl.so  (-DCA_NO_PDL: no programmatic dependent launch)
+  python scripts/build_variants.py trace    -> ctrl_adapter_b200/libctrl_adapter_b200_trace.so  (-DCA_TRACE: role-wait counters)
 
-A/B on the B200:   python bench.py --steps 10 ...   vs   CA_B200_LIB=$PWD/ctrl-adapter_b200/libctrl_adapter_b200_pdl.so python bench.py ...
+A/B on the B200:   python bench.py --steps 10 ...   vs   CA_B200_LIB=$PWD/ctrl_adapter_b200/libctrl_adapter_b200_nopdl.so python bench.py ...
 """
 import os
 import subprocess
@@ -15,8 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "ctrl_adapter_b200")
 sys.path.insert(0, ROOT)
-VARIANTS = {"pdl": ["-DCA_PDL"], "trace": ["-DCA_TRACE"], "pdl_trace": ["-DCA_PDL", "-DCA_TRACE"],
-            "epi": ["-DCA_EXP_EPI"], "all": ["-DCA_PDL", "-DCA_EXP_EPI"]}
+VARIANTS = {"nopdl": ["-DCA_NO_PDL"], "trace": ["-DCA_TRACE"], "nopdl_trace": ["-DCA_NO_PDL", "-DCA_TRACE"]}
 
 
 def build(name):
@@ -38,5 +35,5 @@ def build(name):
 
 
 if __name__ == "__main__":
-    for v in sys.argv[1:] or ["pdl"]:
+    for v in sys.argv[1:] or ["trace"]:
         build(v)

@@ -225,9 +225,12 @@ def _build_pair(make_oracle, make_ours, seed):
     return o, m.to(BF16).eval()
 
 
-def check_step_sdxl(steps=2):
+def check_step_sdxl(steps=2, nsteps=50, b=1, end=1.0, graph=False):
     """Whole SDXL denoising iterations (ControlNet -> adapter -> UNet -> CFG -> Euler) vs the restated reference loop
-    (oracle/pipeline_sdxl.py) in fp32, B=1 at the real 1024x1024 geometry (the 2x adapter only fits 128^2 latents)."""
+    (oracle/pipeline_sdxl.py) in fp32, at the real 1024x1024 geometry (the 2x adapter only fits 128^2 latents).
+    `end` = control_guidance_end (the steps past it run with cond_scale 0, sdxl pipeline :1207-1211, :1346);
+    `graph` steps through CUDA-graph replay (one captured graph per conditioning scale) instead of eager launches."""
+    from ctrl_adapter_b200.loop_base import controlnet_keep
     from ctrl_adapter_b200.adapter import ControlNetAdapter
     from ctrl_adapter_b200.controlnet import ControlNetModel
     from ctrl_adapter_b200.pipeline_sdxl import SDXLControlNetAdapterLoop
@@ -241,7 +244,6 @@ def check_step_sdxl(steps=2):
     ocn, cn = _build_pair(lambda: OC(**cases.CONTROLNET_KW), lambda: ControlNetModel(**cases.CONTROLNET_KW), 4)
     oad, ad = _build_pair(lambda: OA(**cases.ADAPTER_SDXL_KW), lambda: ControlNetAdapter(**cases.ADAPTER_SDXL_KW), 1)
     oun, un = _build_pair(lambda: OU(), lambda: UNet2DConditionModel(), 6)
-    b = 1
     inp = dict(latents=seeded_tensor("s_lat", (b, 4, 128, 128)), prompt_embeds=seeded_tensor("s_pe", (2 * b, 77, 2048)),
                add_text_embeds=seeded_tensor("s_te", (2 * b, 1280)),
                add_time_ids=torch.tensor([[1024.0, 1024, 0, 0, 1024, 1024]] * (2 * b)),
@@ -249,21 +251,26 @@ def check_step_sdxl(steps=2):
                control_images=torch.sigmoid(seeded_tensor("s_img", (2 * b, 3, 512, 512))))
     inp = {k: _q(v).cuda() for k, v in inp.items()}
     sch = EulerDiscreteScheduler()
-    sch.set_timesteps(50, device="cuda")
-    loop = SDXLControlNetAdapterLoop(cn, ad, un, num_inference_steps=50, guidance_scale=5.0)
+    sch.set_timesteps(nsteps, device="cuda")
+    loop = SDXLControlNetAdapterLoop(cn, ad, un, num_inference_steps=nsteps, guidance_scale=5.0, control_guidance_end=end)
     loop.prepare(**inp)
+    keep = controlnet_keep(nsteps, [0.0], [end])
     lat = _q(inp["latents"] * sch.init_noise_sigma)
     with torch.no_grad():
         for i in range(steps):
             lat = sdxl_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["add_text_embeds"], inp["add_time_ids"],
-                            inp["controlnet_prompt_embeds"], inp["control_images"])
-            loop.step(i)
+                            inp["controlnet_prompt_embeds"], inp["control_images"], cond_scale=1.0 * keep[i][0])
+            (loop.step_graph if graph else loop.step)(i)
     torch.cuda.synchronize()
-    return _compare(f"SDXL denoise loop, {steps} steps, B=1 1024x1024", loop.latents, lat, None, tol_rel=2e-2, tol_max=8e-2)
+    return _compare(f"SDXL denoise loop, {steps} of {nsteps} steps, B={b} 1024x1024, guidance_end={end} graph={int(graph)}",
+                    loop.latents, lat, None, tol_rel=2e-2, tol_max=8e-2)
 
 
-def check_step_i2vgen(steps=2, multi=False, sparse=None):
-    """Whole I2VGen-XL iterations (ControlNet[s] -> [router merge] -> adapter -> UNet -> CFG -> DDIM), B=1, F=4, 32^2."""
+def check_step_i2vgen(steps=2, multi=False, sparse=None, f=4, r=32, nsteps=50, end=1.0, graph=False):
+    """Whole I2VGen-XL iterations (ControlNet[s] -> [router merge] -> adapter -> UNet -> CFG -> DDIM), B=1; default F=4,
+    32^2 latents (no 64x64 pooling), r=64 / f=16 is BASELINE config 3's per-clip geometry, r=128 exercises the
+    use_size_512 pooling (i2vgen pipeline :941-947)."""
+    from ctrl_adapter_b200.loop_base import controlnet_keep
     from ctrl_adapter_b200.adapter import ControlNetAdapter, ControlNetRouter
     from ctrl_adapter_b200.controlnet import ControlNetModel, MultiControlNetModel
     from ctrl_adapter_b200.pipeline_i2vgen import I2VGenXLControlNetAdapterLoop
@@ -274,7 +281,8 @@ def check_step_i2vgen(steps=2, multi=False, sparse=None):
     from oracle.pipeline_i2vgen import DDIMScheduler, i2vgen_step
     from oracle.unet_i2vgen import I2VGenXLUNet as OU
     from oracle.weights import seeded_tensor
-    b, f, r = 1, 4, 32
+    b = 1
+    pool = r >= 64  # use_size_512 as the reference has it by default; the 32^2 cases cannot be pooled to 64^2
     kw = dict(cases.ADAPTER_VIDEO_KW, num_frames=f)
     oad, ad = _build_pair(lambda: OA(**kw), lambda: ControlNetAdapter(**kw), 2)
     oun, un = _build_pair(lambda: OU(), lambda: I2VGenXLUNet(), 7)
@@ -298,20 +306,24 @@ def check_step_i2vgen(steps=2, multi=False, sparse=None):
     inp = {k: _q(v).cuda() for k, v in inp.items()}
     images = [_q(i).cuda() for i in images] if multi else _q(images).cuda()
     sch = DDIMScheduler()
-    sch.set_timesteps(50, device="cuda")
-    loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, router, num_inference_steps=50, guidance_scale=9.0,
-                                         inference_expert_masks=masks, sparse_frames=sparse)
+    sch.set_timesteps(nsteps, device="cuda")
+    loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, router, num_inference_steps=nsteps, guidance_scale=9.0,
+                                         use_size_512=pool, inference_expert_masks=masks, sparse_frames=sparse,
+                                         control_guidance_end=end)
     loop.prepare(control_images=images, **inp)
+    keep = controlnet_keep(nsteps, [0.0] * (2 if multi else 1), [end] * (2 if multi else 1))
     lat = inp["latents"]
     with torch.no_grad():
         for i in range(steps):
+            cs = [1.0 * k for k in keep[i]] if multi else 1.0 * keep[i][0]
             lat = i2vgen_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["image_latents"],
                               inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"], images,
-                              router=orouter, masks=masks, sparse_frames=sparse)
-            loop.step(i)
+                              router=orouter, masks=masks, sparse_frames=sparse, use_size_512=pool, cond_scale=cs)
+            (loop.step_graph if graph else loop.step)(i)
     torch.cuda.synchronize()
-    return _compare(f"I2VGen-XL denoise loop multi={int(multi)} sparse={sparse}, {steps} steps, B=1 F=4 32x32", loop.latents_bcfhw(), lat,
-                    None, tol_rel=2e-2, tol_max=8e-2)
+    return _compare(f"I2VGen-XL denoise loop multi={int(multi)} sparse={sparse}, {steps} of {nsteps} steps, B=1 F={f} "
+                    f"{r}x{r} guidance_end={end} graph={int(graph)}", loop.latents_bcfhw(), lat, None, tol_rel=2e-2,
+                    tol_max=8e-2)
 
 
 def check_cfg_euler_v():
@@ -382,7 +394,8 @@ def check_extra_shapes():
     72 x 128 latents and its 36 x 64, 18 x 32 levels; K/V projection shape; folded conditioning convolutions)."""
     from tests import kernel_checks as kc
     kc.RESULTS.clear()
-    recs = [kc.check_attention(1, 5, 2304, 2304, 64), kc.check_attention(2, 10, 576, 576, 64),
+    recs = [kc.check_attention(1, 5, 16384, 16384, 64),  # the dominant SDXL adapter-A shape (128^2 tokens), per sample
+            kc.check_attention(1, 5, 2304, 2304, 64), kc.check_attention(2, 10, 576, 576, 64),
             kc.check_attention(2, 20, 144, 144, 64), kc.check_temporal_attention(2, 14, 144, 10),
             kc.check_conv(2, 36, 64, 320, 320, out_fp32=False, residual=True),
             kc.check_conv(2, 18, 32, 640, 640, out_fp32=False, rowvec=True),
@@ -394,8 +407,10 @@ def check_extra_shapes():
 
 
 def check_controlnet_folded():
-    """ControlNet with CA_FOLD_SMALL_CONV=1 (conditioning-embedding convolutions with pixels folded into channels)."""
-    os.environ["CA_FOLD_SMALL_CONV"] = "1"
+    """ControlNet with CA_FOLD_SMALL_CONV=0: the conditioning-embedding convolutions in their zero-padded form (the
+    folded form -- adjacent pixels in the channel axis -- is the default since round 2 and is what every other ControlNet
+    check exercises)."""
+    os.environ["CA_FOLD_SMALL_CONV"] = "0"
     try:
         return check_controlnet(2, 16)
     finally:
@@ -413,6 +428,12 @@ GROUPS = {
     "shapes": [check_extra_shapes],
     "svd_loop": [check_cfg_euler_v, check_step_svd],  # sparse SVD variant: CPU-emulated only (keeps the GPU suite short)
     "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
+    # round 2: config-1-style 4-step SDXL run crossing control_guidance_end through CUDA-graph replay, a B=2 step at the
+    # config-2 geometry, the router path under graph capture, config 3's F=16 / 64^2 clip, the use_size_512 pooling path
+    # and a video step on either side of control_guidance_end
+    "loops": [lambda: check_step_sdxl(4, nsteps=4, end=0.5, graph=True), lambda: check_step_sdxl(1, b=2),
+              lambda: check_step_i2vgen(1, True, graph=True), lambda: check_step_i2vgen(1, f=16, r=64),
+              lambda: check_step_i2vgen(1, f=2, r=128), lambda: check_step_i2vgen(2, nsteps=2, end=0.5, graph=True)],
 }
 
 

@@ -251,7 +251,7 @@ def router_weights(logits, mask):
     return torch.softmax(lg, dim=-1)
 
 
-def router_merge(xs, w, ptr_table=None):
+def router_merge(xs, w):
     y = None
     for x, wk in zip(xs, w.float()):
         term = _r(x.float() * _r(wk))

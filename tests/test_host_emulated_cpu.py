@@ -188,12 +188,12 @@ def test_emulated_i2vgen_loop_multi_controlnet_router():
     sch = DDIMScheduler()
     sch.set_timesteps(50)
     with emu.patched_ops():
-        loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, router, num_inference_steps=50, guidance_scale=9.0,
+        loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, router, num_inference_steps=50, guidance_scale=9.0, use_size_512=False,
                                              inference_expert_masks=masks)
         loop.prepare(control_images=images, **inp)
         lat = i2vgen_step(ocn, oad, oun, sch, 0, inp["latents"], inp["prompt_embeds"], inp["image_latents"],
                           inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"], images, router=orouter,
-                          masks=masks)
+                          masks=masks, use_size_512=False)
         loop.step(0)
     ours = loop.latents_bcfhw().float()
     rel = float((ours - lat).norm() / lat.norm())
@@ -231,13 +231,13 @@ def test_emulated_i2vgen_loop(sparse):
     sch.set_timesteps(50)
     lat = inp["latents"]
     with emu.patched_ops():
-        loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, None, num_inference_steps=50, guidance_scale=9.0,
+        loop = I2VGenXLControlNetAdapterLoop(cn, ad, un, None, num_inference_steps=50, guidance_scale=9.0, use_size_512=False,
                                              sparse_frames=sparse)
         loop.prepare(control_images=images, **inp)
         for i in range(2):
             lat = i2vgen_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["image_latents"],
                               inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"], images,
-                              sparse_frames=sparse)
+                              sparse_frames=sparse, use_size_512=False)
             loop.step(i)
     ours = loop.latents_bcfhw().float()
     rel = float((ours - lat).norm() / lat.norm())

@@ -214,3 +214,47 @@ def test_reference_import_paths_resolve():
         ControlNetHelper()
     with pytest.raises(NotImplementedError):
         save_as_gif([], "x.gif")
+
+
+def test_controlnet_keep_is_the_reference_formula():
+    """loop_base.controlnet_keep / control_scale against the literal comprehension of the reference
+    (sdxl_controlnet_adapter_pipeline.py:1207-1211, :1296-1302) for the shipped settings (start 0, end 0.5 / 0.6 / 1)."""
+    from ctrl_adapter_b200.loop_base import DenoiseLoopBase, controlnet_keep
+    for n, s, e in [(50, 0.0, 0.5), (50, 0.0, 0.6), (25, 0.0, 0.4), (4, 0.0, 0.5), (50, 0.2, 1.0), (7, 0.1, 0.9)]:
+        ref = [[1.0 - float(i / n < s_ or (i + 1) / n > e_) for s_, e_ in zip([s], [e])] for i in range(n)]
+        assert controlnet_keep(n, [s], [e]) == ref
+    loop = DenoiseLoopBase()
+    loop.num_inference_steps = 50
+    loop._init_control(0.75, 0.0, 0.6, 1)
+    assert [loop.control_scale(i) for i in (0, 29, 30, 49)] == [0.75, 0.75, 0.0, 0.0]
+    loop._init_control([1.0, 0.5], 0.0, [1.0, 0.5], 2)  # Multi-ControlNet: one keep per net, scale stays a tuple
+    assert loop.control_scale(10) == (1.0, 0.5) and loop.control_scale(40) == (1.0, 0.0)
+
+
+def test_static_context_cache_hits_only_the_registered_tensor():
+    """Attention.cache_static / cache_static_context: the stored K/V is used for the registered tensor OBJECT while it is
+    unmodified, and recomputed for a clone, after an in-place update, and after the weights change."""
+    from tests import ops_emulator as emu
+    from ctrl_adapter_b200.layers import Attention, cache_static_context
+    torch.manual_seed(0)
+    att = Attention(128, 96, 2, 64).to(torch.bfloat16)
+    x = torch.randn(2, 16, 128).to(torch.bfloat16)
+    ctx = torch.randn(2, 5, 96).to(torch.bfloat16)
+    calls = []
+    with emu.patched_ops():
+        orig = att.project_kv
+        att.project_kv = lambda c: (calls.append(1), orig(c))[1]
+        assert cache_static_context(att, ctx) == 1 and len(calls) == 1
+        y0 = att(x, ctx=ctx)
+        assert len(calls) == 1                       # hit
+        y1 = att(x, ctx=ctx.clone())
+        assert len(calls) == 2                       # another tensor object: recomputed
+        assert torch.equal(y0, y1)
+        ctx.mul_(2.0)
+        y2 = att(x, ctx=ctx)
+        assert len(calls) == 3 and not torch.equal(y0, y2)   # in-place update seen through _version
+        cache_static_context(att, ctx)
+        with torch.no_grad():
+            att.to_q.weight.add_(1.0)                # first parameter changes -> _key() changes -> stale entry ignored
+        att(x, ctx=ctx)
+        assert len(calls) == 5
