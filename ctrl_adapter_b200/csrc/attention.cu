@@ -39,7 +39,7 @@
 
 namespace ca {
 
-static constexpr int kSplitDefault = 2;  // softmax warpgroups per CTA (column halves of a score row) for head dim 64
+static constexpr int kSplitDefault = 1;  // softmax warpgroups per CTA (column halves of a score row) for head dim 64
 static constexpr int kPolyDefault = 2;  // pairs out of every 8 whose exp2 runs on the FMA pipe instead of MUFU
 static constexpr int kTileQ = 128;
 static constexpr int kTileKV = 128;
@@ -393,18 +393,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           tmem_st_wait();
         }
       }
-      // P of tile j-1 must have been consumed by its PV MMA before it is overwritten
-      if (j > 0 && !waited_o) {
-        TR_WAIT(tr_o_full, mbar_wait(o_full, (g - 1) & 1));
-        tc_fence_after();
-      }
       // ---- pass 2: p = exp2(s*sl2 - m_used*sl2) (<= 2^8), row sum, bf16 P, 32 columns at a time ----
       const float mneg = -m_used * sl2;
       const uint64_t sl2_2 = pack_f32x2(sl2, sl2), mneg_2 = pack_f32x2(mneg, mneg);
       uint64_t rs = pack_f32x2(0.f, 0.f);
+      uint32_t pw[kChunks][16];  // packed bf16 P of the whole row (half): kept until the previous PV has released P
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
-        uint32_t pw[16];
         if (MASK && c >= nch) {
           if (c == kChunks - 1) {  // the S buffer is released by the last chunk's turn even when that chunk is empty
             tc_fence_before();
@@ -412,7 +407,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) mbar_arrive(s_empty);
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pw[i] = 0u;  // P = 0 for keys that do not exist
+          for (int i = 0; i < 16; ++i) pw[c][i] = 0u;  // P = 0 for keys that do not exist
         } else {
           uint32_t sc[32];
           tmem_ld_32x32(tmem_s + lane_sel + s_col + c * 32, sc);
@@ -437,11 +432,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               p1 = fast_exp2(x1);
             }
             rs = add_f32x2(rs, pack_f32x2(p0, p1));
-            pw[i >> 1] = pack_bf16x2(p0, p1);
+            pw[c][i >> 1] = pack_bf16x2(p0, p1);
           }
         }
-        // P goes to tensor memory (the PV MMA reads its A operand from there): no shared-memory stores, no proxy fence
-        tmem_st_32x16(tmem_p + lane_sel + p_cell + c * 16, pw);
       }
       {
         float rs0, rs1;
@@ -449,6 +442,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         l_run += rs0 + rs1;
       }
       if (tr_me) TR_EVT(22);
+      // P of tile j-1 must have been consumed by its PV MMA before it is overwritten (waiting here, after the
+      // exponentials, the PV issued at the end of the previous tile has long retired)
+      if (j > 0 && !waited_o) {
+        TR_WAIT(tr_o_full, mbar_wait(o_full, (g - 1) & 1));
+        tc_fence_after();
+      }
+      // P goes to tensor memory (the PV MMA reads its A operand from there): no shared-memory stores, no proxy fence
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) tmem_st_32x16(tmem_p + lane_sel + p_cell + c * 16, pw[c]);
       tmem_st_wait();
       tc_fence_before();         // orders the tcgen05.st (P, and O of a rescale) before the MMA that follows the barrier
       __syncwarp();

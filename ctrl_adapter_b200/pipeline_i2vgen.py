@@ -65,6 +65,11 @@ class I2VGenXLControlNetAdapterLoop(DenoiseLoopBase):
         self.fps = fps.float().contiguous()
         self.cn_embeds = controlnet_prompt_embeds.to(BF16).contiguous()
         self._pool = (h, w) != (64, 64) and self.use_size_512                              # :941-947
+        if self._pool:
+            # the reference pools the ControlNet input to 64x64 here, but its video adapters do not up-sample, so the
+            # 64x64 residuals cannot be added to a UNet running at another size (it fails inside the UNet, :689)
+            raise ValueError("use_size_512=True needs 64x64 latents (512x512 video) for the I2VGen-XL backbone; pass "
+                             "use_size_512=False to run the ControlNet at the latent resolution")
 
         def prep_image(img):
             img = img.to(BF16).contiguous()

@@ -225,7 +225,7 @@ def _build_pair(make_oracle, make_ours, seed):
     return o, m.to(BF16).eval()
 
 
-def check_step_sdxl(steps=2, nsteps=50, b=1, end=1.0, graph=False):
+def check_step_sdxl(steps=2, nsteps=50, b=1, end=1.0, graph=False, eager_ref=False):
     """Whole SDXL denoising iterations (ControlNet -> adapter -> UNet -> CFG -> Euler) vs the restated reference loop
     (oracle/pipeline_sdxl.py) in fp32, at the real 1024x1024 geometry (the 2x adapter only fits 128^2 latents).
     `end` = control_guidance_end (the steps past it run with cond_scale 0, sdxl pipeline :1207-1211, :1346);
@@ -256,20 +256,32 @@ def check_step_sdxl(steps=2, nsteps=50, b=1, end=1.0, graph=False):
     loop.prepare(**inp)
     keep = controlnet_keep(nsteps, [0.0], [end])
     lat = _q(inp["latents"] * sch.init_noise_sigma)
+    args = (inp["prompt_embeds"], inp["add_text_embeds"], inp["add_time_ids"], inp["controlnet_prompt_embeds"],
+            inp["control_images"])
     with torch.no_grad():
         for i in range(steps):
-            lat = sdxl_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["add_text_embeds"], inp["add_time_ids"],
-                            inp["controlnet_prompt_embeds"], inp["control_images"], cond_scale=1.0 * keep[i][0])
+            lat = sdxl_step(ocn, oad, oun, sch, i, lat, *args, cond_scale=1.0 * keep[i][0])
             (loop.step_graph if graph else loop.step)(i)
     torch.cuda.synchronize()
+    # the same trajectory as the reference runs it: bf16 modules under autocast, bf16 latents (the error budget of a
+    # multi-step trajectory is whatever that path accumulates against the fp32 truth)
+    eager = None
+    if eager_ref:
+        e = [m.to(BF16) for m in (ocn, oad, oun)]
+        el = _q(inp["latents"] * sch.init_noise_sigma).to(BF16)
+        a16 = [t.to(BF16) if t.is_floating_point() else t for t in args]
+        with torch.no_grad(), torch.autocast("cuda", dtype=BF16):
+            for i in range(steps):
+                el = sdxl_step(*e, sch, i, el, *a16, cond_scale=1.0 * keep[i][0]).to(BF16)
+        eager = el.float()
     return _compare(f"SDXL denoise loop, {steps} of {nsteps} steps, B={b} 1024x1024, guidance_end={end} graph={int(graph)}",
-                    loop.latents, lat, None, tol_rel=2e-2, tol_max=8e-2)
+                    loop.latents, lat, eager, tol_rel=2e-2 if eager is None else 6e-2, tol_max=8e-2 if eager is None else 0.2)
 
 
-def check_step_i2vgen(steps=2, multi=False, sparse=None, f=4, r=32, nsteps=50, end=1.0, graph=False):
+def check_step_i2vgen(steps=2, multi=False, sparse=None, f=4, r=32, nsteps=50, end=1.0, graph=False, eager_ref=False):
     """Whole I2VGen-XL iterations (ControlNet[s] -> [router merge] -> adapter -> UNet -> CFG -> DDIM), B=1; default F=4,
-    32^2 latents (no 64x64 pooling), r=64 / f=16 is BASELINE config 3's per-clip geometry, r=128 exercises the
-    use_size_512 pooling (i2vgen pipeline :941-947)."""
+    32^2 latents (use_size_512 off), r=64 / f=16 is BASELINE config 3's per-clip geometry with use_size_512 on as the
+    reference has it (the reference's pooling to 64^2 at any other size yields residuals the video UNet cannot add)."""
     from ctrl_adapter_b200.loop_base import controlnet_keep
     from ctrl_adapter_b200.adapter import ControlNetAdapter, ControlNetRouter
     from ctrl_adapter_b200.controlnet import ControlNetModel, MultiControlNetModel
@@ -282,7 +294,7 @@ def check_step_i2vgen(steps=2, multi=False, sparse=None, f=4, r=32, nsteps=50, e
     from oracle.unet_i2vgen import I2VGenXLUNet as OU
     from oracle.weights import seeded_tensor
     b = 1
-    pool = r >= 64  # use_size_512 as the reference has it by default; the 32^2 cases cannot be pooled to 64^2
+    pool = r == 64  # use_size_512 as the reference has it by default (an identity at 64^2)
     kw = dict(cases.ADAPTER_VIDEO_KW, num_frames=f)
     oad, ad = _build_pair(lambda: OA(**kw), lambda: ControlNetAdapter(**kw), 2)
     oun, un = _build_pair(lambda: OU(), lambda: I2VGenXLUNet(), 7)
@@ -313,17 +325,27 @@ def check_step_i2vgen(steps=2, multi=False, sparse=None, f=4, r=32, nsteps=50, e
     loop.prepare(control_images=images, **inp)
     keep = controlnet_keep(nsteps, [0.0] * (2 if multi else 1), [end] * (2 if multi else 1))
     lat = inp["latents"]
+    args = (inp["prompt_embeds"], inp["image_latents"], inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"])
+    scale_of = lambda i: [1.0 * k for k in keep[i]] if multi else 1.0 * keep[i][0]  # noqa: E731
     with torch.no_grad():
         for i in range(steps):
-            cs = [1.0 * k for k in keep[i]] if multi else 1.0 * keep[i][0]
-            lat = i2vgen_step(ocn, oad, oun, sch, i, lat, inp["prompt_embeds"], inp["image_latents"],
-                              inp["image_embeddings"], inp["fps"], inp["controlnet_prompt_embeds"], images,
-                              router=orouter, masks=masks, sparse_frames=sparse, use_size_512=pool, cond_scale=cs)
+            lat = i2vgen_step(ocn, oad, oun, sch, i, lat, *args, images, router=orouter, masks=masks,
+                              sparse_frames=sparse, use_size_512=pool, cond_scale=scale_of(i))
             (loop.step_graph if graph else loop.step)(i)
     torch.cuda.synchronize()
+    eager = None
+    if eager_ref and not multi:
+        e = [m.to(BF16) for m in (ocn, oad, oun)]
+        el = inp["latents"].to(BF16)
+        a16 = [t.to(BF16) if t.is_floating_point() else t for t in args]
+        with torch.no_grad(), torch.autocast("cuda", dtype=BF16):
+            for i in range(steps):
+                el = i2vgen_step(*e, sch, i, el, *a16, images.to(BF16), sparse_frames=sparse, use_size_512=pool,
+                                 cond_scale=scale_of(i)).to(BF16)
+        eager = el.float()
     return _compare(f"I2VGen-XL denoise loop multi={int(multi)} sparse={sparse}, {steps} of {nsteps} steps, B=1 F={f} "
-                    f"{r}x{r} guidance_end={end} graph={int(graph)}", loop.latents_bcfhw(), lat, None, tol_rel=2e-2,
-                    tol_max=8e-2)
+                    f"{r}x{r} guidance_end={end} graph={int(graph)}", loop.latents_bcfhw(), lat, eager,
+                    tol_rel=2e-2 if eager is None else 6e-2, tol_max=8e-2 if eager is None else 0.2)
 
 
 def check_cfg_euler_v():
@@ -429,11 +451,13 @@ GROUPS = {
     "svd_loop": [check_cfg_euler_v, check_step_svd],  # sparse SVD variant: CPU-emulated only (keeps the GPU suite short)
     "step": [check_step_sdxl, lambda: check_step_i2vgen(2, False), lambda: check_step_i2vgen(1, True)],
     # round 2: config-1-style 4-step SDXL run crossing control_guidance_end through CUDA-graph replay, a B=2 step at the
-    # config-2 geometry, the router path under graph capture, config 3's F=16 / 64^2 clip, the use_size_512 pooling path
-    # and a video step on either side of control_guidance_end
-    "loops": [lambda: check_step_sdxl(4, nsteps=4, end=0.5, graph=True), lambda: check_step_sdxl(1, b=2),
+    # config-2 geometry, the router path under graph capture, config 3's F=16 / 64^2 clip and a video step on either
+    # side of control_guidance_end
+    # (whole few-step trajectories are judged like the modules: no worse than 1.5x the error the reference's own eager
+    # bf16-autocast trajectory accumulates against the fp32 truth, since a 2- or 4-step schedule amplifies rounding)
+    "loops": [lambda: check_step_sdxl(4, nsteps=4, end=0.5, graph=True, eager_ref=True), lambda: check_step_sdxl(1, b=2),
               lambda: check_step_i2vgen(1, True, graph=True), lambda: check_step_i2vgen(1, f=16, r=64),
-              lambda: check_step_i2vgen(1, f=2, r=128), lambda: check_step_i2vgen(2, nsteps=2, end=0.5, graph=True)],
+              lambda: check_step_i2vgen(2, nsteps=2, end=0.5, graph=True, eager_ref=True)],
 }
 
 

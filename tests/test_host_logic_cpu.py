@@ -192,19 +192,19 @@ def test_pretrained_folder_roundtrip(tmp_path):
 
 
 def test_reference_import_paths_resolve():
-    """the module paths inference.py imports exist and resolve to the B200-backed classes (or, for the
-    out-of-scope helpers, to stubs that fail loudly when used)."""
+    """the module paths AND NAMES inference.py imports (:351-367) exist and resolve to the B200-backed
+    classes (or, for the out-of-scope helpers, to stubs that fail loudly when used)."""
     import argparse
     from controlnet.controlnet import ControlNetModel  # noqa: F401
     from controlnet.multicontrolnet import MultiControlNetModel  # noqa: F401
     from i2vgen_xl.models.unets.unet_i2vgen_xl import I2VGenXLUNet  # noqa: F401
-    from i2vgen_xl.pipelines.i2vgen_xl_controlnet_adapter_pipeline import I2VGenXLControlNetAdapterLoop  # noqa: F401
+    from i2vgen_xl.pipelines.i2vgen_xl_controlnet_adapter_pipeline import I2VGenXLControlNetAdapterPipeline  # noqa: F401
     from model.ctrl_adapter import ControlNetAdapter  # noqa: F401
     from model.ctrl_helper import ControlNetHelper
     from model.ctrl_router import ControlNetRouter  # noqa: F401
-    from sdxl.pipelines.sdxl_controlnet_adapter_pipeline import SDXLControlNetAdapterLoop  # noqa: F401
+    from sdxl.pipelines.sdxl_controlnet_adapter_pipeline import SDXLControlNetAdapterPipeline  # noqa: F401
     from svd.models.unets.unet_spatio_temporal_condition import UNetSpatioTemporalConditionModel  # noqa: F401
-    from svd.pipelines.svd_controlnet_adapter_pipeline import SVDControlNetAdapterLoop  # noqa: F401
+    from svd.pipelines.svd_controlnet_adapter_pipeline import SVDControlNetAdapterPipeline  # noqa: F401
     from utils.utils import bool_flag, center_crop_and_resize, save_as_gif, save_concatenated_gif  # noqa: F401
     assert ControlNetAdapter is A.ControlNetAdapter
     assert bool_flag("True") is True and bool_flag("off") is False
@@ -258,3 +258,36 @@ def test_static_context_cache_hits_only_the_registered_tensor():
             att.to_q.weight.add_(1.0)                # first parameter changes -> _key() changes -> stale entry ignored
         att(x, ctx=ctx)
         assert len(calls) == 5
+
+
+def test_pipeline_classes_mirror_the_reference_signatures():
+    """The three pipeline classes take the reference's constructor and __call__ parameters, in the reference's order
+    (names extracted from /root/reference with ast by the snippet in tests/golden/README, committed as
+    tests/golden/reference_pipeline_signatures.json); ours may only APPEND keyword extensions."""
+    import inspect
+    import json
+    import os
+    from ctrl_adapter_b200 import pipelines as P
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_pipeline_signatures.json")))
+    for cls_name, fns in ref.items():
+        cls = getattr(P, cls_name)
+        for fn, names in fns.items():
+            ours = [n for n in inspect.signature(getattr(cls, fn)).parameters if n not in ("self", "kwargs")]
+            assert ours[: len(names)] == names, (cls_name, fn, [a for a in zip(ours, names) if a[0] != a[1]][:3])
+            if fn == "__init__":
+                assert len(ours) == len(names)
+
+
+def test_pipeline_needs_pre_encoded_inputs_without_encoders():
+    """Without encoder components the pipeline asks for the pre-encoded tensors instead of silently doing something
+    else; component registry / to() / from_pretrained error path."""
+    from ctrl_adapter_b200 import pipelines as P
+    pipe = P.SDXLControlNetAdapterPipeline(vae=None, text_encoder=None, text_encoder_2=None, tokenizer=None,
+                                           tokenizer_2=None, unet=torch.nn.Linear(1, 1), scheduler=None, adapter=None,
+                                           helper=None, controlnet=torch.nn.Linear(1, 1))
+    assert set(pipe.components) >= {"unet", "controlnet", "adapter", "helper", "vae"}
+    assert pipe.to(torch.float32) is pipe and pipe.device.type == "cpu"
+    with pytest.raises(ValueError, match="prompt_embeds"):
+        pipe(prompt="a cat", control_images=torch.zeros(1, 3, 512, 512))
+    with pytest.raises(FileNotFoundError):
+        P.SDXLControlNetAdapterPipeline.from_pretrained("/nonexistent/snapshot", controlnet=None, adapter=None, helper=None)
