@@ -60,6 +60,15 @@ def timestep_vector(timestep, n: int, device) -> torch.Tensor:
     return t.reshape(-1).contiguous()
 
 
+def shared_timestep(timestep, device) -> torch.Tensor:
+    """The step's ONE timestep as a [1] fp32 device tensor.  Every kernel path here shares a single timestep across the
+    batch (the pipelines pass a 0-dim `t`); a tensor with several entries would be silently truncated, so it is refused
+    instead (checking that the entries are equal would cost a host sync per call)."""
+    if isinstance(timestep, torch.Tensor) and timestep.numel() > 1:
+        raise NotImplementedError("per-sample timesteps: pass the step's single timestep (0-dim / 1-element / number)")
+    return timestep_vector(timestep, 1, device)[:1].contiguous()
+
+
 class AlphaBlender(Packable):
     """Learned mix factor; alpha = sigmoid(mix_factor) in the parameter dtype (image_only_indicator is all zeros on
     this path, adapter_spatial_temporal.py:200).  The blend itself is fused into the producing GEMM's epilogue."""
@@ -206,7 +215,7 @@ class AdapterSpatioTemporal(nn.Module):
             raise NotImplementedError("released adapters always have the spatial resnet and transformer")
         if self.add_temporal_resnet != self.add_temporal_transformer:
             raise NotImplementedError("temporal resnet / transformer are enabled together in the released configs")
-        t1 = t[:1].contiguous()  # every frame-sample shares the step's timestep
+        t1 = t[:1].contiguous()  # every frame-sample shares the step's timestep (forward() refuses anything else)
         for i in range(self.num_layers):
             # resnet time embedding: Timesteps(bf16-rounded t) -> MLP -> SiLU (shared by both resnets)
             temb = self.resnet_time_embedding(ops.timestep_embedding(t1, c, round_t_bf16=True))
@@ -221,7 +230,11 @@ class AdapterSpatioTemporal(nn.Module):
             hcur = self.proj_in(tok).reshape(n, hw, self.inner_dim)
             blk = self.spatial_attentions[i]
             if ctx.shape[1] == 1:
-                # single-token context (video path, i2vgen pipeline :1048): cross attention == broadcast vector
+                # single-token context (video path, i2vgen pipeline :1048): cross attention == broadcast vector.  The
+                # pipelines pass ONE row ([1, 1, D]) for all samples; several distinct rows are refused, not truncated
+                if ctx.shape[0] != 1:
+                    raise NotImplementedError("single-token context: pass one [1, 1, D] row shared by every sample "
+                                              "(image_embeddings[-1].unsqueeze(0) in the reference pipelines)")
                 hcur = blk.attn1(blk.norm1.layer_norm(hcur), residual=hcur)
                 cv = blk.attn2.single_token_output(ctx.reshape(-1, ctx.shape[-1])[:1].contiguous(), src=ctx)
                 n3, hsum = blk.norm3.layer_norm(hcur.reshape(n * hw, -1), add_rowvec=cv, rows_per_vec=n * hw,
@@ -241,7 +254,7 @@ class AdapterSpatioTemporal(nn.Module):
 
     def forward(self, hidden_states, num_frames: int, timestep=None, encoder_hidden_states=None, sparsity_masking=None):
         x = to_channels_last_bf16(hidden_states)
-        t = timestep_vector(timestep, x.shape[0], x.device)
+        t = shared_timestep(timestep, x.device)
         ctx = _prep_ctx(encoder_hidden_states)
         return as_nchw(self.forward_nhwc(x, num_frames, t, ctx))
 
@@ -333,7 +346,7 @@ class ControlNetAdapter(PretrainedMixin, nn.Module):
         ids = self.get_down_block_ids()
         dev = down_block_res_samples[0].device
         n = down_block_res_samples[0].shape[0]
-        t = timestep_vector(timestep, n, dev)
+        t = shared_timestep(timestep, dev)
         ctx = _prep_ctx(encoder_hidden_states)
         out: List[torch.Tensor] = []
         cur = 0
@@ -359,7 +372,7 @@ class ControlNetAdapter(PretrainedMixin, nn.Module):
         if mid_block_res_sample is None or self.mid_block_adapter is None:
             return None
         x = to_channels_last_bf16(mid_block_res_sample)
-        t = timestep_vector(timestep, x.shape[0], x.device)
+        t = shared_timestep(timestep, x.device)
         return as_nchw(self.mid_block_adapter.forward_nhwc(x, num_frames, t, _prep_ctx(encoder_hidden_states)))
 
 

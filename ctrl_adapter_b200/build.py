@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libctrl_adapter_b200.so")
 SOURCES = ["gemm_conv.cu", "gemm_conv_bn64.cu", "gemm_conv_bn128.cu", "gemm_conv_bn160.cu", "gemm_conv_bn256.cu", "gemm_conv_wide.cu",
-           "attention.cu", "norm.cu", "elementwise.cu", "capi.cu"]
+           "attention.cu", "temporal_attention.cu", "norm.cu", "elementwise.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 

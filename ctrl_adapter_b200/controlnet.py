@@ -14,7 +14,7 @@ from torch import nn
 
 from . import ops
 from .persistence import PretrainedMixin
-from .adapter import _ConfigDict, as_nchw, timestep_vector, to_channels_last_bf16
+from .adapter import _ConfigDict, as_nchw, shared_timestep, to_channels_last_bf16
 from .layers import BF16, Conv2d, ResnetBlock2D, TimestepEmbedding, Transformer2DModel
 from .ops import ACT_SILU
 
@@ -177,7 +177,7 @@ class ControlNetModel(PretrainedMixin, nn.Module):
         dev = sample.device
         c0 = self.config.block_out_channels[0]
         # 1. time (exact t -- unlike the adapter the ControlNet does not round t to bf16; controlnet.py:751-758)
-        t = timestep_vector(timestep, n, dev)[:1].contiguous()
+        t = shared_timestep(timestep, dev)
         emb = self.time_embedding(ops.timestep_embedding(t, c0, flip_sin_to_cos=self.flip_sin_to_cos,
                                                          freq_shift=float(self.freq_shift)))
         temb_act = ops.silu(emb)

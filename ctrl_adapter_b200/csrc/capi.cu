@@ -341,10 +341,32 @@ int ca_i2vgen_latent_encoder(const void* x, int32_t clips, int32_t frames, int64
 }
 int ca_temporal_attention(const void* q, const void* k, const void* v, int32_t clips, int32_t frames, int64_t hw,
                           int32_t heads, float scale, int64_t in_row_stride, void* out, void* s) {
-  CA_LAUNCH(ca::launch_temporal_attention((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                          clips, frames, hw, heads, scale, in_row_stride, (__nv_bfloat16*)out,
-                                          (cudaStream_t)s),
-            "temporal_attention");
+  cudaStream_t stream = static_cast<cudaStream_t>(s);
+  if (clips < 1 || frames < 1 || frames > 32 || hw < 1 || heads < 1) return fail(CA_ERR_INVALID, "empty temporal attention problem");
+  if ((in_row_stride & 7) != 0) return fail(CA_ERR_INVALID, "row stride must be a multiple of 8 elements");
+  static const bool fma = getenv("CA_TATTN_FMA") != nullptr;  // developer A/B knob: round 1's FMA kernel
+  if (fma) {
+    CA_LAUNCH(ca::launch_temporal_attention((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                                            clips, frames, hw, heads, scale, in_row_stride, (__nv_bfloat16*)out, stream),
+              "temporal_attention");
+  }
+  // global dims ordered (channel, frame, pixel, clip): a box then holds whole frame sequences of consecutive pixels
+  const int seq = frames <= 16 ? 16 : 32;
+  const cuuint64_t dims[4] = {(cuuint64_t)heads * 64, (cuuint64_t)frames, (cuuint64_t)hw, (cuuint64_t)clips};
+  const cuuint64_t st[3] = {(cuuint64_t)hw * in_row_stride * 2, (cuuint64_t)in_row_stride * 2,
+                            (cuuint64_t)frames * hw * in_row_stride * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)seq, (cuuint32_t)(128 / seq), 1};
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap(&tq, q, 4, dims, st, box);
+  if (rc) return rc;
+  if ((rc = make_tmap(&tk, k, 4, dims, st, box))) return rc;
+  if ((rc = make_tmap(&tv, v, 4, dims, st, box))) return rc;
+  ca::TemporalAttnParams p;
+  p.clips = clips; p.frames = frames; p.heads = heads; p.hw = hw;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.out_row_stride = static_cast<long long>(heads) * 64;
+  CA_LAUNCH(ca::launch_temporal_attention_tc(tq, tk, tv, p, stream), "temporal_attention");
 }
 
 }  // extern "C"

@@ -57,6 +57,17 @@ struct AttnParams {
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream);
 
+// --- temporal_attention.cu ---
+struct TemporalAttnParams {
+  int clips, frames, heads;
+  long long hw;
+  float scale_log2;            // softmax scale * log2(e)
+  __nv_bfloat16* out;          // rows ((clip * frames + f) * hw + pixel), heads * 64 used columns
+  long long out_row_stride;    // elements
+};
+cudaError_t launch_temporal_attention_tc(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v,
+                                         const TemporalAttnParams& p, cudaStream_t stream);
+
 // --- norm.cu ---
 cudaError_t launch_gn_stats(const __nv_bfloat16* x0, int c0, const __nv_bfloat16* x1, int c1, int n, long long hw,
                             int groups, double* sums /*[n][groups][2], zeroed by the launcher*/, cudaStream_t stream);

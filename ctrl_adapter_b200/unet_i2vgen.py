@@ -18,7 +18,7 @@ from torch import nn
 
 from . import ops
 from .persistence import PretrainedMixin
-from .adapter import _ConfigDict, timestep_vector, to_channels_last_bf16
+from .adapter import _ConfigDict, shared_timestep, to_channels_last_bf16
 from .layers import (cache_static_context, BF16, Attention, BasicTransformerBlock, Conv2d, FeedForward, Linear, Norm, Packable, ResnetBlock2D,
                      TemporalConv, TimestepEmbedding, Transformer2DModel)
 from .ops import ACT_SILU
@@ -288,7 +288,7 @@ class I2VGenXLUNet(PretrainedMixin, nn.Module):
         cond = self._conditioning(fps, image_latents, image_embeddings, encoder_hidden_states)
         n = b * f
         dev = sample.device
-        t = timestep_vector(timestep, b, dev)[:1].contiguous()
+        t = shared_timestep(timestep, dev)
         t_emb = self.time_embedding(ops.timestep_embedding(t, 320))            # [1, 1280]
         emb = ops.add(t_emb.expand(b, -1).contiguous(), cond["fps_emb"])       # [b, 1280]
         if b > 1:

@@ -14,7 +14,7 @@ from torch import nn
 
 from . import ops
 from .persistence import PretrainedMixin
-from .adapter import _ConfigDict, as_nchw, timestep_vector, to_channels_last_bf16
+from .adapter import _ConfigDict, as_nchw, shared_timestep, to_channels_last_bf16
 from .layers import BF16, Conv2d, Norm, ResnetBlock2D, TimestepEmbedding, Transformer2DModel
 
 
@@ -150,7 +150,7 @@ class UNet2DConditionModel(PretrainedMixin, nn.Module):
         if sample.shape[-1] % 4 != 0 or sample.shape[-2] % 4 != 0:
             raise NotImplementedError("latent resolution must be a multiple of 4")
         # time + SDXL micro-conditioning embedding
-        t = timestep_vector(timestep, n, dev)[:1].contiguous()
+        t = shared_timestep(timestep, dev)
         t_emb = self.time_embedding(ops.timestep_embedding(t, 320, flip_sin_to_cos=self.flip_sin_to_cos,
                                                            freq_shift=float(self.freq_shift)))  # [1, 1280]
         text_embeds = added_cond_kwargs["text_embeds"].to(BF16)

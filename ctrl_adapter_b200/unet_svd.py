@@ -21,7 +21,7 @@ from torch import nn
 
 from . import ops
 from .persistence import PretrainedMixin
-from .adapter import (AlphaBlender, TemporalBasicTransformerBlock, TemporalResnetBlock, _ConfigDict, timestep_vector,
+from .adapter import (AlphaBlender, TemporalBasicTransformerBlock, TemporalResnetBlock, _ConfigDict, shared_timestep,
                       to_channels_last_bf16)
 from .layers import BF16, BasicTransformerBlock, Conv2d, Linear, Norm, ResnetBlock2D, TimestepEmbedding
 
@@ -244,7 +244,7 @@ class UNetSpatioTemporalConditionModel(PretrainedMixin, nn.Module):
         if encoder_hidden_states.shape[1] != 1:
             raise NotImplementedError("the SVD backbone is driven with one image-embedding token per clip")
         # 1. time: one timestep for the whole batch (:393-406) + per-sample added_time_ids embedding (:414-418)
-        t = timestep_vector(timestep, b, dev)[:1].contiguous()
+        t = shared_timestep(timestep, dev)
         t_emb = self.time_embedding(ops.timestep_embedding(t, 320))  # [1, 1280]
         ids = added_time_ids.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         tid = ops.timestep_embedding(ids, self.config.addition_time_embed_dim).reshape(b, -1).contiguous()

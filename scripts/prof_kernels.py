@@ -50,6 +50,14 @@ elif which.startswith("conv"):  # conv or conv:<bn>
     bias = torch.zeros(320, device=dev)
     fn = lambda: ops.conv2d(x, w, bias, bn=bn)  # noqa: E731
     flops = 2.0 * 16 * 128 * 128 * 2880 * 320
+elif which.startswith("tattn"):  # temporal attention at config 3's adapter-A shape (8 clips x 16 frames x 64^2 pixels, 5 heads)
+    clips, frames, hw, heads = {"tattn": (8, 16, 4096, 5), "tattn14": (4, 14, 9216, 5), "tattn20": (8, 16, 256, 20)}[which]
+    inner = heads * 64
+    qkv = rnd(clips * frames * hw, 3 * inner)
+    fn = lambda: ops.temporal_attention(qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:], clips, frames, hw,  # noqa: E731
+                                        heads, 0.125, row_stride=3 * inner)
+    flops = 4.0 * clips * hw * heads * frames * frames * 64
+    nbytes = 4.0 * clips * frames * hw * inner * 2
 elif which == "ln":
     x = rnd(16384, 1280)
     g, b = torch.ones(1280, device=dev), torch.zeros(1280, device=dev)
@@ -75,4 +83,5 @@ if do_time:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print(f"{which}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s")
+    extra = f"  {nbytes / ms / 1e6:.0f} GB/s" if which.startswith("tattn") else ""
+    print(f"{which}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s{extra}")

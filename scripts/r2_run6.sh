@@ -1,5 +1,10 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
+timeout 600 python -m tests.kernel_checks --group attn > gpurun_out/r2_attn_tc.log 2>&1
+echo "attn group rc=$?"; grep -c "\[ok" gpurun_out/r2_attn_tc.log; grep "temporal\|FAIL\|EXC" gpurun_out/r2_attn_tc.log | cut -c1-300
+for s in tattn tattn14 tattn20; do CA_TATTN_FMA=1 timeout 120 python scripts/prof_kernels.py $s --time 2>&1 | tail -1 | sed "s/^/fma /"; timeout 120 python scripts/prof_kernels.py $s --time 2>&1 | tail -1 | sed "s/^/tc  /"; done | tee gpurun_out/r2_tattn.txt
+timeout 600 python -m tests.module_checks --groups video,shapes > gpurun_out/r2_video_tc.log 2>&1
+echo "video,shapes rc=$?"; grep "^\[" gpurun_out/r2_video_tc.log | cut -c1-200
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_sdxl_run6.json 2> gpurun_out/r2_bench_sdxl_run6.err
 echo "bench sdxl rc=$?"; tail -2 gpurun_out/r2_bench_sdxl_run6.err
 for w in i2vgen svd multi; do
