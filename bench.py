@@ -292,6 +292,30 @@ def measured_peaks():
 # ----------------------------------------------------------------------------------------------------
 # CPU legs: the oracle (restated reference PyTorch path) on the host cores
 # ----------------------------------------------------------------------------------------------------
+def _cpu_threads():
+    """Threads for the CPU legs: one per PHYSICAL core this process may run on, whatever OMP_NUM_THREADS says (torchrun
+    sets it to 1).  BASELINE.md section 3 says os.cpu_count(), but on the pool's 2-way SMT hosts 128 logical threads
+    make the oracle 34x SLOWER than 64 (218 s vs 6.4 s for the same 512x512 frame-sample, round-2 run 6 vs round 1:
+    OpenMP spin-waits fighting over the shared cores), so the reference's CPU path would be misrepresented."""
+    try:
+        allowed = os.sched_getaffinity(0)
+        cores, phys, cid, cpu = set(), None, None, None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("processor"):
+                cpu = int(line.split(":")[1])
+            elif line.startswith("physical id"):
+                phys = int(line.split(":")[1])
+            elif line.startswith("core id"):
+                cid = int(line.split(":")[1])
+                if cpu in allowed:
+                    cores.add((phys, cid))
+        if cores:
+            return len(cores)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
 def _cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -338,10 +362,10 @@ def _oracle_flops_per_frame_sample(res):
 def cpu_quick_sdxl_rate(res, budget_s, sample_res=512):
     """The cpu_baseline leg of the DEFAULT run (must stay well inside a minute; a full-resolution pass of the reference
     path costs ~190 s on the pool's hosts): ONE SDXL frame-sample at `sample_res` (ControlNet -> adapter -> UNet, fp32
-    eager, os.cpu_count() threads), >= 3 timed passes after one warm-up, scaled to the 16-frame-sample `res` step by the
+    eager, one thread per physical core), >= 3 timed passes after one warm-up, scaled to the 16-frame-sample `res` step by the
     exact FLOP ratio (torch FlopCounterMode on meta tensors).  `--impl reference` times the un-scaled full-resolution
     sample instead; both state their extrapolation factor."""
-    cores = os.cpu_count() or 1
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     t0 = time.time()
@@ -378,20 +402,18 @@ def cpu_quick_sdxl_rate(res, budget_s, sample_res=512):
                       f"reference path (the reference itself needs diffusers, not installable here); cpu: {_cpu_model()}",
             "s_per_sample_median": med, "s_per_sample_min": mn, "value_from_min": 1.0 / (mn * factor),
             "extrapolation_factor": factor, "timed_passes": len(times), "cpu_tflops": f_pass / med / 1e12,
-            "model_build_s": build_s, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")}
+            "model_build_s": build_s, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "logical_cpus": os.cpu_count()}
     return rate, info
 
 
 def cpu_reference_step_rate(workload, res, steps, warmup, budget_s):
-    """Oracle on the host CPU: fp32 eager, torch.set_num_threads(os.cpu_count()) whatever
-    OMP_NUM_THREADS says.  A full step of any workload costs many CPU-minutes, so a timed pass is a BOUNDED sample of the
+    """Oracle on the host CPU: fp32 eager, one thread per physical core (_cpu_threads) whatever OMP_NUM_THREADS says.  A full step of any workload costs many CPU-minutes, so a timed pass is a BOUNDED sample of the
     same workload at its real resolution and frame count: one denoising iteration of ONE batch element (sdxl: one image
     = 2 CFG frame-samples at `res`; video: one clip = 2 x F frame-samples).  Batch elements are independent on this path
     (no op mixes samples), so the step time is the sample time x the per-GPU batch -- the only extrapolation, stated in
-    `sample`.  (Measured on the pool's 128-thread hosts: ~190 s per SDXL pass, 0.1 TFLOP/s -- the fp32 16384-token
-    attention of the reference path is what the CPU spends it on -- so usually ONE pass fits the budget.)  At least 3 timed passes unless the budget runs out; min and median are both reported, `value` uses the
+    `sample`.  At least 3 timed passes unless the budget runs out; min and median are both reported, `value` uses the
     median."""
-    cores = os.cpu_count() or 1
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     w = WORKLOADS[workload]
     batch = w["batch"]
@@ -426,7 +448,7 @@ def cpu_reference_step_rate(workload, res, steps, warmup, budget_s):
                       f"reference itself needs diffusers, not installable here); cpu: {_cpu_model()}",
             "s_per_sample_median": med, "s_per_sample_min": mn, "value_from_min": 1.0 / (mn * batch),
             "extrapolation_factor": batch, "timed_passes": len(times), "cpu_tflops": n_fs * w["tflop"] / med,
-            "model_build_s": build_s, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")}
+            "model_build_s": build_s, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "logical_cpus": os.cpu_count()}
     return rate, info
 
 
@@ -627,7 +649,7 @@ def main():
     eager_gpu = None
     del loop
     torch.cuda.empty_cache()
-    if not a.skip_eager_baseline and rank == 0:
+    if not a.skip_eager_baseline and rank == 0 and world == 1:  # N > 1 lines: see the N = 1 line of the same workload
         try:
             estep, lat = build_oracle_stepper(a.workload, inp, dev, BF16, batch)
 
