@@ -339,6 +339,9 @@ int ca_i2vgen_latent_encoder(const void* x, int32_t clips, int32_t frames, int64
   CA_LAUNCH(ca::launch_i2vgen_latent_encoder((const __nv_bfloat16*)x, clips, frames, hw, c_stride, params,
                                              (__nv_bfloat16*)y, (cudaStream_t)s), "i2vgen_latent_encoder");
 }
+int ca_softmax_rows(const float* x, int64_t rows, int64_t cols, void* y, void* s) {
+  CA_LAUNCH(ca::launch_softmax_rows(x, rows, cols, (__nv_bfloat16*)y, (cudaStream_t)s), "softmax_rows");
+}
 int ca_temporal_attention(const void* q, const void* k, const void* v, int32_t clips, int32_t frames, int64_t hw,
                           int32_t heads, float scale, int64_t in_row_stride, void* out, void* s) {
   cudaStream_t stream = static_cast<cudaStream_t>(s);

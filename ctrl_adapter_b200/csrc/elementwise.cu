@@ -497,6 +497,60 @@ cudaError_t launch_i2vgen_latent_encoder(const __nv_bfloat16* x, int clips, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row softmax, fp32 scores -> bf16 probabilities: the VAE decoder's single 512-wide attention head (diffusers
+// AutoencoderKL mid block) is run as  S = Q K^T (tensor-core GEMM, fp32 out)  ->  this kernel  ->  O = P V (GEMM); its
+// head dim is outside attention_kernel's 64 / 128 / 192 and it runs once per generation, not per step.  One CTA per
+// row, three passes over the row (max, sum, write); the row (<= 64 KB) stays in L1 / L2 between them.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, long long cols, __nv_bfloat16* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
+  __shared__ float red[8];
+  const float4* row = reinterpret_cast<const float4*>(x + static_cast<long long>(blockIdx.x) * cols);
+  uint2* out = reinterpret_cast<uint2*>(y + static_cast<long long>(blockIdx.x) * cols);
+  const long long nv = cols >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto block_reduce = [&](float v, bool is_max) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = is_max ? fmaxf(v, t) : v + t;
+    }
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    v = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) v = is_max ? fmaxf(v, red[i]) : v + red[i];
+    return v;
+  };
+  float m = -INFINITY;
+  for (long long i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row[i];
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  m = block_reduce(m, true);
+  float l = 0.f;
+  for (long long i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row[i];
+    l += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+  }
+  l = block_reduce(l, false);
+  const float inv = 1.0f / l;
+  for (long long i = threadIdx.x; i < nv; i += 256) {
+    const float4 v = row[i];
+    out[i] = make_uint2(pack_bf16x2(__expf(v.x - m) * inv, __expf(v.y - m) * inv),
+                        pack_bf16x2(__expf(v.z - m) * inv, __expf(v.w - m) * inv));
+  }
+}
+cudaError_t launch_softmax_rows(const float* x, long long rows, long long cols, __nv_bfloat16* y, cudaStream_t stream) {
+  if (rows < 1 || rows > 0x7fffffffLL || cols < 4 || (cols & 3) != 0) return cudaErrorInvalidValue;
+  CA_KERNEL_LAUNCH(softmax_rows_kernel, static_cast<unsigned>(rows), 256, 0, stream, x, cols, y);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Temporal self-attention: sequence = the F frames of one pixel, head dim 64.  HBM-bound (every Q/K/V element is read
 // once), so plain FMA.  One warp per (clip, pixel, head).
 //   frames <= 16: lane = (query frame i = lane >> 1, half = lane & 1 of the head dim): each lane holds q[i][32 dims],

@@ -516,7 +516,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_const
               for (int j = 0; j < 32; j += 2) {
                 v[j] *= p.out_scale;
                 v[j + 1] *= p.out_scale;
-                round2_bf16(v[j], v[j + 1]);
+                if (!p.out_fp32) round2_bf16(v[j], v[j + 1]);  // fp32 output (attention scores of the VAE): unrounded
               }
             }
             if (p.rowvec != nullptr && row_ok) {

@@ -94,6 +94,7 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* x, int n, int h, int w, int c
                               cudaStream_t stream);
 cudaError_t launch_router_weights(const float* logits, const unsigned char* mask, int nrouters, int nexperts,
                                   float* weights, cudaStream_t stream);
+cudaError_t launch_softmax_rows(const float* x, long long rows, long long cols, __nv_bfloat16* y, cudaStream_t stream);
 static constexpr int kMaxRouterExperts = 8;
 cudaError_t launch_router_merge(const __nv_bfloat16* const* xs_host, const float* w, int nactive, long long n,
                                 __nv_bfloat16* y, cudaStream_t stream);

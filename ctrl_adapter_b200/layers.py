@@ -344,13 +344,13 @@ class ResnetBlock2D(nn.Module):
     """GN-SiLU-[2x up]-conv3x3 (+temb) - GN-SiLU-conv3x3 (+1x1 shortcut) -- model/resnet_block_2d.py:164-221.
     Two-source input (x, x2) implements the UNet skip concat without materialising it."""
 
-    def __init__(self, cin: int, cout: int, temb_channels: int, eps: float, use_in_shortcut: Optional[bool] = None,
-                 up: bool = False):
+    def __init__(self, cin: int, cout: int, temb_channels: Optional[int], eps: float,
+                 use_in_shortcut: Optional[bool] = None, up: bool = False):
         super().__init__()
         self.up = up
         self.norm1 = Norm(cin, eps)
         self.conv1 = Conv2d(cin, cout, 3)
-        self.time_emb_proj = Linear(temb_channels, cout)
+        self.time_emb_proj = Linear(temb_channels, cout) if temb_channels is not None else None  # None: VAE resnets
         self.norm2 = Norm(cout, eps)
         self.conv2 = Conv2d(cout, cout, 3)
         shortcut = (cin != cout) if use_in_shortcut is None else use_in_shortcut
@@ -358,7 +358,7 @@ class ResnetBlock2D(nn.Module):
 
     def forward(self, x, temb_act, x2=None, temb_proj=None):
         """temb_act: SiLU(temb) [N, T] (shared by all resnets of a model) or a precomputed projection."""
-        if temb_proj is None:
+        if temb_proj is None and self.time_emb_proj is not None:
             temb_proj = self.time_emb_proj(temb_act)
         h = self.norm1.group_norm(x, x2=x2, silu=True, up2x=self.up)
         h = self.conv1(h, rowvec=temb_proj)

@@ -510,6 +510,15 @@ def upsample2x(x: torch.Tensor):
     return y
 
 
+def softmax_rows(x: torch.Tensor):
+    """fp32 [rows, cols] -> bf16 softmax over the last axis (fp32 math, one rounding)."""
+    _req(x, torch.float32)
+    rows, cols = x.shape
+    y = torch.empty((rows, cols), device=x.device, dtype=BF16)
+    _launch("softmax_rows", 0.0, 6.0 * x.numel(), "ca_softmax_rows", x.data_ptr(), rows, cols, y.data_ptr(), _stream())
+    return y
+
+
 def router_weights(logits: torch.Tensor, mask: Optional[torch.Tensor]):
     """logits [R, E] fp32, mask [E] uint8 (0 = masked) -> softmax weights [R, E] fp32."""
     _req(logits, torch.float32)

@@ -12,8 +12,9 @@ section 8f) and is *duck-typed*: a pipeline uses whatever ``text_encoder`` / ``h
 objects it was constructed with (e.g. the diffusers / transformers ones where those libraries exist), and when one is
 absent the caller passes that stage's OUTPUT instead -- ``prompt_embeds`` ... exactly as the reference signature already
 allows, plus the keyword-only extensions listed in each ``__call__`` (``controlnet_prompt_embeds``, ``image_embeddings``,
-``image_latents``, tensor ``control_images``).  ``output_type="latent"`` needs no VAE.  Nothing here falls back to a
-PyTorch implementation of the hot path.
+``image_latents``, tensor ``control_images``).  ``output_type="latent"`` needs no VAE; with
+``vae=ctrl_adapter_b200.vae.AutoencoderKL`` the SDXL and I2VGen-XL pipelines decode on the B200 kernels as well.  Nothing
+here falls back to a PyTorch implementation of the hot path.
 """
 from __future__ import annotations
 
@@ -27,6 +28,8 @@ from .controlnet import MultiControlNetModel
 from .pipeline_i2vgen import I2VGenXLControlNetAdapterLoop
 from .pipeline_sdxl import SDXLControlNetAdapterLoop
 from .pipeline_svd import SVDControlNetAdapterLoop
+from .vae import decode_latents, tensor2vid
+from .vae import postprocess as vae_postprocess
 
 BF16 = torch.bfloat16
 
@@ -271,10 +274,11 @@ class SDXLControlNetAdapterPipeline(DiffusionPipeline):
         if output_type == "latent":
             image = latents
         else:
-            vae = _vae(self)
-            image = vae.decode(latents / vae.config.scaling_factor, return_dict=False)[0]
+            vae = _vae(self)  # ctrl_adapter_b200.vae.AutoencoderKL, or any object with diffusers' decode() / config
+            image = vae.decode(latents / vae.config.scaling_factor, return_dict=False)[0]           # :1414
             proc = getattr(self, "image_processor", None)
-            image = proc.postprocess(image, output_type=output_type) if proc is not None else image
+            image = proc.postprocess(image, output_type=output_type) if proc is not None else \
+                vae_postprocess(image, output_type)
         if not return_dict:
             return (image,)
         return StableDiffusionXLPipelineOutput(images=image), None, None  # (:1433) no router on the SDXL path
@@ -365,9 +369,7 @@ class I2VGenXLControlNetAdapterPipeline(DiffusionPipeline):
         if output_type == "latent":
             video = latents
         else:
-            _vae(self)
-            decode = _need(getattr(self, "decode_latents", None), "a decode_latents method / output_type='latent'", "VAE")
-            video = decode(latents, decode_chunk_size=decode_chunk_size)
+            video = tensor2vid(decode_latents(_vae(self), latents, decode_chunk_size), output_type)  # :398-418, :1134-1135
         if not return_dict:
             return (video,)
         return I2VGenXLPipelineOutput(frames=video, down_block_weights=weights[0], mid_block_weights=weights[1])
@@ -448,8 +450,11 @@ class SVDControlNetAdapterPipeline(DiffusionPipeline):
         if output_type == "latent":
             frames = latents
         else:
+            # SVD decodes with AutoencoderKLTemporalDecoder (svd pipeline :265-292), a different model that this package
+            # does not contain: a user-supplied pipeline-level decode_latents is used when present
             _vae(self)
-            decode = _need(getattr(self, "decode_latents", None), "a decode_latents method / output_type='latent'", "VAE")
+            decode = _need(getattr(self, "decode_latents", None), "a decode_latents method / output_type='latent'",
+                           "temporal VAE decoder")
             frames = decode(latents, f, decode_chunk_size)
         if not return_dict:
             return frames

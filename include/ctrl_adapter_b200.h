@@ -164,6 +164,10 @@ int ca_upsample2x(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, voi
  */
 int ca_router_weights(const float* logits, const uint8_t* mask, int32_t nrouters, int32_t nexperts, float* weights,
                       void* cuda_stream);
+/* Row softmax, fp32 [rows, cols] -> bf16 probabilities (cols % 4 == 0): the VAE decoder's single 512-wide attention
+ * head (diffusers AutoencoderKL mid block, reached from sdxl pipeline :1414 / i2vgen pipeline :398-418) runs as
+ * GEMM (QK^T, fp32) -> this -> GEMM (PV).  softmax in fp32, one rounding to bf16 (torch SDPA math semantics). */
+int ca_softmax_rows(const float* x, int64_t rows, int64_t cols, void* y, void* cuda_stream);
 /* Weighted merge of expert residuals (i2vgen_xl pipeline :1001-1022): y = sum_e w[e] * xs[e], bf16 rounding
  * after each multiply and each add as in the reference loop.  xs: HOST array of nactive (<= 8) device pointers; they
  * travel to the kernel by value, so the call is CUDA-graph capturable. */

@@ -224,6 +224,16 @@ def check_attention(b, heads, lq, lk, d, seed=0, ramp=0.0):
     return rec
 
 
+def check_softmax_rows(rows, cols, seed=0):
+    ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(seed + 9)
+    x = (torch.randn(rows, cols, generator=g) * 4.0).cuda()
+    x[0, :7] = 30.0  # a few dominant scores in one row
+    out = ops.softmax_rows(x)
+    torch.cuda.synchronize()
+    return _report(f"softmax_rows {rows}x{cols}", out, torch.softmax(x, dim=-1), 2 ** -8, 1e-6)
+
+
 def check_temporal_attention(clips, frames, hw, heads, seed=0):
     ops = _ops()
     c = heads * 64
@@ -443,6 +453,8 @@ def run_all(stop_on_fail=False, group=None):
         lambda: check_layernorm(1000, 512),
         lambda: check_layernorm(400, 320, add=True),
         lambda: check_layernorm(64, 1280),
+        lambda: check_softmax_rows(300, 4096),
+        lambda: check_softmax_rows(64, 16384),
         check_timestep_embedding,
         check_layout_pool,
         check_router,

@@ -211,6 +211,24 @@ def check_unet_svd(b=2, f=4, r=32, with_residuals=True):
                     eager, tol_rel=3e-2, tol_max=8e-2)
 
 
+def check_vae(n=2, r=32):
+    """AutoencoderKL.decode at the published SDXL width (latents r x r -> images 8r x 8r) vs the restated diffusers
+    decoder: fp32 truth and its eager bf16-autocast run."""
+    from ctrl_adapter_b200.vae import AutoencoderKL
+    from oracle.vae import AutoencoderKL as OV
+    from oracle.weights import seeded_tensor
+    inputs = dict(z=seeded_tensor("vae_z", (n, 4, r, r)))
+    call = lambda m, i: m.decode(i["z"])[0]  # noqa: E731
+    sd, ref, eager, inp16 = _oracle_runs(lambda: OV(), 11, inputs, call)
+    with torch.device("cuda"):
+        ours_m = AutoencoderKL()
+    ours_m.load_state_dict(sd)
+    ours_m = ours_m.to(BF16).cuda().eval()
+    ours = ours_m.decode(inp16["z"]).sample
+    torch.cuda.synchronize()
+    return _compare(f"AutoencoderKL.decode n={n} latents {r}x{r}", ours, ref, eager, tol_rel=3e-2, tol_max=8e-2)
+
+
 def _build_pair(make_oracle, make_ours, seed):
     """oracle (fp32, bf16-quantised weights, on GPU) and our module with identical weights."""
     from oracle.weights import seeded_init_
@@ -444,6 +462,7 @@ GROUPS = {
     "controlnet": [lambda: check_controlnet(2, 8), lambda: check_controlnet(2, 16, True, 0.75)],
     "unet": [lambda: check_unet_sdxl(2, 16, True), lambda: check_unet_sdxl(1, 32, False)],
     "video": [lambda: check_unet_i2vgen(1, 4, 32, True), lambda: check_unet_i2vgen(2, 2, 32, False)],
+    "vae": [lambda: check_vae(2, 32), lambda: check_vae(1, 64)],
     "svd": [lambda: check_unet_svd(2, 4, 32, True), lambda: check_unet_svd(1, 3, 16, False)],
     "sparse": [lambda: check_step_i2vgen(2, False, sparse=[0, 2])],
     "fold": [check_controlnet_folded],

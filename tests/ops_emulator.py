@@ -28,6 +28,7 @@ def _r(x: torch.Tensor) -> torch.Tensor:
 def _epilogue(acc, bias, act, out_scale, rowvec, residual, blend_src, blend_alpha, out_fp32):
     v = acc if bias is None else acc + bias.float()
     if out_fp32:
+        v = v * out_scale if out_scale != 1.0 else v
         return v if residual is None else v + residual.float()
     v = _r(v)
     if act == ACT_SILU:
@@ -244,6 +245,10 @@ def i2vgen_latent_encoder(x, clips, frames, params):
     return out
 
 
+def softmax_rows(x):
+    return torch.softmax(x.float(), dim=-1).to(BF16)
+
+
 def router_weights(logits, mask):
     lg = logits.float().clone()
     if mask is not None:
@@ -323,7 +328,7 @@ def cfg_ddim(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None
 
 _EMULATED = ["linear", "conv2d", "temporal_conv", "attention", "temporal_attention", "group_norm", "layer_norm",
              "timestep_embedding", "silu", "add", "nchw_to_nhwc", "nhwc_to_nchw", "avgpool", "upsample2x", "i2vgen_latent_encoder",
-             "router_weights", "router_merge", "cfg_euler", "cfg_euler_v", "cfg_ddim"]
+             "softmax_rows", "router_weights", "router_merge", "cfg_euler", "cfg_euler_v", "cfg_ddim"]
 
 
 @contextlib.contextmanager

@@ -119,6 +119,35 @@ def test_emulated_controlnet_folded_small_convs(monkeypatch):
     assert float((a - b).abs().max()) <= 2.0 ** -7 * float(a.abs().max())
 
 
+def test_emulated_vae_decoder():
+    """AutoencoderKL.decode (the VAE after the loop, sdxl pipeline :1414) through the emulated op layer vs the restated
+    diffusers decoder: block wiring, the 512-wide single-head attention as GEMM -> softmax -> GEMM, 4 -> 8 channel
+    padding of the latent / post_quant_conv / conv_out, state-dict keys (encoder.* keys of a checkpoint are skipped)."""
+    from ctrl_adapter_b200.vae import AutoencoderKL, decode_latents, postprocess, tensor2vid
+    from oracle.vae import AutoencoderKL as OV
+    from oracle.weights import seeded_tensor
+    kw = dict(block_out_channels=(32, 64, 64, 64), layers_per_block=1)
+    o = seeded_init_(OV(**kw), 11).eval()
+    m = AutoencoderKL(**kw)
+    sd = dict(o.state_dict())
+    sd["encoder.conv_in.weight"] = torch.zeros(1)  # a published checkpoint also carries the encoder half
+    m.load_state_dict(sd)
+    for p_ in o.parameters():
+        p_.data = _q(p_.data)
+    m = m.to(BF16).eval()
+    z = _q(seeded_tensor("vae_z", (2, 4, 8, 8)))
+    with torch.no_grad(), emu.patched_ops():
+        ref = o.decode(z)[0]
+        out = m.decode(z).sample
+        vid = decode_latents(m, z.reshape(1, 2, 4, 8, 8).permute(0, 2, 1, 3, 4) * m.config.scaling_factor)
+    assert out.shape == ref.shape == (2, 3, 64, 64)
+    rel = float((out.float() - ref).norm() / ref.norm())
+    assert rel <= 3e-2, rel
+    assert vid.shape == (1, 3, 2, 64, 64) and float((vid[0].permute(1, 0, 2, 3) - out.float()).abs().max()) == 0.0
+    assert postprocess(out, "np").shape == (2, 64, 64, 3) and len(postprocess(out, "pil")) == 2
+    assert tensor2vid(vid, "pt").shape == (1, 2, 3, 64, 64)
+
+
 @pytest.mark.slow
 def test_emulated_unet_svd():
     """Two clips with DIFFERENT image tokens + 5-D residuals with surplus entries: covers the per-clip broadcast rows and

@@ -14,7 +14,7 @@ def _need_gpu():
         pytest.fail("GPU tests selected but no CUDA device is visible (there is no CPU fallback to test)")
 
 
-@pytest.mark.parametrize("group", ["adapter", "controlnet", "unet", "video", "step", "loops"])
+@pytest.mark.parametrize("group", ["adapter", "controlnet", "unet", "video", "vae", "step", "loops"])
 def test_module_group(group):
     res = mc.run(group)
     bad = [r for r in res if not r["ok"]]
