@@ -210,8 +210,11 @@ def test_reference_import_paths_resolve():
     assert bool_flag("True") is True and bool_flag("off") is False
     with pytest.raises(argparse.ArgumentTypeError):
         bool_flag("maybe")
+    helper = ControlNetHelper()  # no hub access: constructed without a text encoder
     with pytest.raises(NotImplementedError):
-        ControlNetHelper()
+        helper.add_depth_estimator()
+    with pytest.raises(NotImplementedError):
+        helper.encode_controlnet_prompt("a cat", "cpu", 1, True)
     with pytest.raises(NotImplementedError):
         save_as_gif([], "x.gif")
 
@@ -291,3 +294,44 @@ def test_pipeline_needs_pre_encoded_inputs_without_encoders():
         pipe(prompt="a cat", control_images=torch.zeros(1, 3, 512, 512))
     with pytest.raises(FileNotFoundError):
         P.SDXLControlNetAdapterPipeline.from_pretrained("/nonexistent/snapshot", controlnet=None, adapter=None, helper=None)
+
+
+def test_helper_prepare_images_batched_and_prompt_encoding():
+    """ControlNetHelper.prepare_images (ctrl_helper.py:268-296) for PIL / ndarray / tensor frames and batch sizes > 1, and
+    encode_controlnet_prompt (:301-457) on a duck-typed tokenizer / text encoder."""
+    import numpy as np
+    from PIL import Image
+    from ctrl_adapter_b200.helper import ControlNetHelper
+    h = ControlNetHelper()
+    rng = np.random.default_rng(0)
+    frames = [Image.fromarray(rng.integers(0, 255, (40, 60, 3), dtype=np.uint8)) for _ in range(3)]
+    out = h.prepare_images(frames, 32, 16, batch_size=2, num_images_per_prompt=1, device="cpu", dtype=torch.float32,
+                           do_classifier_free_guidance=True)
+    assert out.shape == (2, 6, 3, 16, 32) and 0.0 <= float(out.min()) and float(out.max()) <= 1.0
+    assert torch.equal(out[0], out[1]) and torch.equal(out[0, :3], out[0, 3:])   # CFG copy, batch repeat
+    ref0 = np.array(frames[0].convert("RGB").resize((32, 16), resample=Image.LANCZOS)).astype(np.float32) / 255.0
+    assert np.allclose(out[0, 0].permute(1, 2, 0).numpy(), ref0)
+    t = h.prepare_images([torch.rand(3, 16, 32), rng.random((16, 32, 3)).astype(np.float32)], 32, 16, 1, 1, "cpu",
+                         torch.float32)
+    assert t.shape == (1, 2, 3, 16, 32)
+
+    class Tok:
+        model_max_length = 5
+
+        def __call__(self, text, padding, max_length, truncation, return_tensors):
+            text = [text] if isinstance(text, str) else text
+            ids = torch.tensor([[len(s) % 7] * max_length for s in text])
+            return type("E", (), {"input_ids": ids, "attention_mask": torch.ones_like(ids)})()
+
+    class Enc(torch.nn.Module):
+        dtype = torch.float32
+
+        def forward(self, ids, attention_mask=None, output_hidden_states=False):
+            e = ids.float().unsqueeze(-1).repeat(1, 1, 4)
+            return (e, e.mean(1))
+
+    h2 = ControlNetHelper(text_encoder=Enc(), tokenizer=Tok())
+    pe, ne, pp, npp = h2.encode_controlnet_prompt(["ab", "abc"], "cpu", 2, True)
+    assert pe.shape == (4, 5, 4) and ne.shape == (4, 5, 4) and pp.shape == (4, 4) and npp.shape == (4, 4)
+    assert float(ne.abs().max()) == 0.0 and float(pe[0, 0, 0]) == 2.0 and float(pe[2, 0, 0]) == 3.0
+    assert h2._get_add_time_ids((1024, 1024), (0, 0), (1024, 1024), torch.float32).shape == (1, 6)
