@@ -117,7 +117,7 @@ cudaError_t launch_gn_stats(const __nv_bfloat16* x0, int c0, const __nv_bfloat16
 // 4 independent 16-byte loads in flight, no index arithmetic beyond one add per pixel, no shared-memory reads.
 // ---------------------------------------------------------------------------------------------
 template <bool SILU, bool UP>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1, int h,
                 int w, int imgs_per_sample, int groups, float eps, const double* __restrict__ sums,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int pix_per_block,
@@ -186,13 +186,30 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
     }
   };
 
+  // software pipeline: the four loads of the NEXT step are issued before the current four pixels are normalised (SiLU is
+  // ~30 instructions per pixel-vector), so a thread always has loads in flight -- without it the kernel sat at ~3.5 TB/s
+  // with half of its threads computing and not loading at any time
   int pix = p_begin + rsub;
-  for (; pix + 3 * rows_per_iter < p_end; pix += 4 * rows_per_iter) {
-    uint4 u[4];
+  const int step = 4 * rows_per_iter;
+  uint4 u[4];
+  bool have = pix + 3 * rows_per_iter < p_end;
+  if (have) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) u[k] = ld_nc(src + static_cast<long long>(pix + k * rows_per_iter) * cs);
+  }
+  while (have) {
+    uint4 cur[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) emit(u[k], pix + k * rows_per_iter);
+    for (int k = 0; k < 4; ++k) cur[k] = u[k];
+    const int pn = pix + step;
+    have = pn + 3 * rows_per_iter < p_end;
+    if (have) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ld_nc(src + static_cast<long long>(pn + k * rows_per_iter) * cs);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) emit(cur[k], pix + k * rows_per_iter);
+    pix = pn;
   }
   for (; pix < p_end; pix += rows_per_iter) emit(ld_nc(src + static_cast<long long>(pix) * cs), pix);
 }
@@ -245,10 +262,13 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
   CA_PDL_TRIGGER();
   CA_PDL_WAIT();
   const int warps_per_block = blockDim.x >> 5;
-  const long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nvec = c >> 3;
+  // resident warps walk the rows with a grid-wide stride (round 2): one-row-per-warp blocks lived ~1.5 us each and the
+  // SM spent half of the time re-filling its block slots (warps active 52 % in profiles/r1_ncu_ln.md)
+  const long long row_stride = static_cast<long long>(gridDim.x) * warps_per_block;
+  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < rows;
+       row += row_stride) {
   const __nv_bfloat16* xr = x + row * c;
   [[maybe_unused]] const __nv_bfloat16* av = RV ? add_rowvec + (row / rows_per_vec) * c : nullptr;
   uint4 u[NV];
@@ -328,6 +348,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
       *reinterpret_cast<uint4*>(y + row * c + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
+  }  // row loop
 }
 
 cudaError_t launch_layernorm(const __nv_bfloat16* x, long long rows, int c, float eps, const float* gamma,
@@ -335,7 +356,16 @@ cudaError_t launch_layernorm(const __nv_bfloat16* x, long long rows, int c, floa
                              __nv_bfloat16* y_sum, __nv_bfloat16* y, cudaStream_t stream) {
   if ((c & 7) != 0 || c > 8 * 32 * 8) return cudaErrorInvalidValue;
   const int warps = 8;
-  const unsigned blocks = static_cast<unsigned>((rows + warps - 1) / warps);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+  }
+  const int nv0 = ((c >> 3) + 31) / 32;
+  const long long resident = static_cast<long long>(sms) * (nv0 <= 5 ? 5 : 3);  // matches the kernel's launch bounds
+  const long long need = (rows + warps - 1) / warps;
+  const unsigned blocks = static_cast<unsigned>(need < resident ? need : resident);
   const long long rpv = rows_per_vec > 0 ? rows_per_vec : 1;
   const int nv = ((c >> 3) + 31) / 32;
 #define CA_LN(NV)                                                                                                      \
