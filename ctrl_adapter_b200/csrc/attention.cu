@@ -29,8 +29,8 @@
 //     warpgroup 0 keeps 48 -- with fewer the MMA issuer spills its descriptors and every tcgen05.mma issue costs hundreds
 //     of cycles) so the scores of a row (half) stay in registers without spills while two CTAs still share an SM;
 //   * the producer / MMA warps back off with nanosleep while blocked so their polling does not steal issue slots.
-// With head dim 64 the CTA uses 113 KB smem / 256 TMEM columns, so two CTAs share an SM and one CTA's softmax overlaps
-// the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3 (one CTA per SM).
+// With head dim 64 the CTA uses 101 KB smem (two Q buffers, two K and two V tiles) / 256 TMEM columns, so two CTAs share
+// an SM and one CTA's softmax overlaps the other's MMAs.  Head dims 128/192 (the zero-padded ControlNet heads) use DQ = 2/3 (one CTA per SM).
 #include <cstdlib>
 #include <type_traits>
 
@@ -50,11 +50,15 @@ template <int DQ>
 struct AttnCfg {
   static constexpr int kStages = 2;
   static constexpr uint32_t kQBytes = DQ * kChunkBytes;
-  static constexpr uint32_t kPBytes = 2 * kChunkBytes;  // no longer holds P (tensor memory does): row max / row sum exchange
+  // Q is double buffered (round 2) where shared memory allows: with a single buffer the load of the next item's Q tile
+  // could only start when this item's last QK^T had retired, and its ~2 us of HBM latency was exposed once per work item
+  // -- which is most of an item when there is ONE KV tile (the 77-key cross attention ran at 0.3 of its HBM bound)
+  static constexpr int kQStages = (DQ <= 2) ? 2 : 1;
+  static constexpr uint32_t kPBytes = 4096;  // row max / row sum exchange of the NS = 2 variant (P itself lives in TMEM)
   static constexpr uint32_t kStageBytes = (DQ + 1) * kChunkBytes;  // K chunks + one V slice
   // data + 1024: the slack serves both the 1024-byte alignment of the swizzled tiles and the mbarriers.
   // For DQ == 1 this is 115712 B, i.e. exactly two CTAs per SM: 2 x (115712 + 1024 reserved) = 233472 = 228 KB.
-  static constexpr uint32_t kDataBytes = kQBytes + kPBytes + kStages * kStageBytes;
+  static constexpr uint32_t kDataBytes = kQStages * kQBytes + kPBytes + kStages * kStageBytes;
   static constexpr uint32_t kSmemBytes = kDataBytes + 1024;
   static constexpr uint32_t kTmemCols = 256;
 };
@@ -120,16 +124,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
-  if (pad + Cfg::kDataBytes + 128 > Cfg::kSmemBytes) __trap();  // barriers would not fit behind the tiles
+  if (pad + Cfg::kDataBytes + 192 > Cfg::kSmemBytes) __trap();  // barriers would not fit behind the tiles
   constexpr int kCols = kTileKV / NS;     // score columns per softmax thread
   constexpr int kChunks = kCols / 32;     // 32-column TMEM loads per thread and tile
   uint8_t* smem_q = smem;
-  uint8_t* smem_p = smem + Cfg::kQBytes;
+  uint8_t* smem_p = smem + Cfg::kQStages * Cfg::kQBytes;
   [[maybe_unused]] float* xch_max = reinterpret_cast<float*>(smem_p);          // [2 tile parities][2 halves][128 rows]
   [[maybe_unused]] float* xch_sum = reinterpret_cast<float*>(smem_p) + 512;    // [2 halves][128 rows]
   uint8_t* smem_kv = smem_p + Cfg::kPBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* q_full = bars + 0;
+  uint64_t* q_full = bars + 14;   // [2]
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* k_empty = bars + 3;   // [2]
   uint64_t* v_full = bars + 10;   // [2]
@@ -138,8 +142,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* s_empty = bars + 6;
   uint64_t* p_full = bars + 7;
   uint64_t* o_full = bars + 8;
-  uint64_t* q_empty = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* q_empty = bars + 16;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -163,8 +167,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -207,10 +213,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++it) {
         decode(w, q0, b, h, vs);
         const int kvb = b / p.kv_batch_div;
-        mbar_wait_backoff(q_empty, (it & 1) ^ 1, p.backoff_ns);  // every QK^T of the previous item has retired
+        const int qs = it % Cfg::kQStages;
+        // every QK^T of the item that used this Q buffer (one or two items ago) has retired
+        mbar_wait_backoff(&q_empty[qs], ((it / Cfg::kQStages) & 1) ^ 1, p.backoff_ns);
         TR_EVT(1);
-        mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
-        for (int c = 0; c < DQ; ++c) tma_load_3d(smem_q + c * kChunkBytes, &tmap_q, q_full, h * dpad + c * 64, q0, b);
+        mbar_arrive_expect_tx(&q_full[qs], Cfg::kQBytes);
+        for (int c = 0; c < DQ; ++c)
+          tma_load_3d(smem_q + qs * Cfg::kQBytes + c * kChunkBytes, &tmap_q, &q_full[qs], h * dpad + c * 64, q0, b);
         load_k(0, g, kvb);
         TR_EVT(2);
         for (int j = 0; j < nkv; ++j, ++g) {
@@ -230,7 +239,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V tile) is MN-major
-      const uint32_t q_addr = smem_u32(smem_q);
+      const uint32_t q_base = smem_u32(smem_q);
       TR_DECL(tr_kv_full);
       TR_DECL(tr_s_empty);
       TR_DECL(tr_p_full);
@@ -243,7 +252,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // QK^T of global tile gq (tile jq of item itq); waits for that item's Q when jq == 0
       auto issue_qk = [&](uint32_t gq, int jq, uint32_t itq) {
         const int st = gq & 1;
-        if (jq == 0) TR_WAIT(tr_q_full, mbar_wait_backoff(q_full, itq & 1, p.backoff_ns));
+        const int qs = itq % Cfg::kQStages;
+        const uint32_t q_addr = q_base + qs * Cfg::kQBytes;
+        if (jq == 0) TR_WAIT(tr_q_full, mbar_wait_backoff(&q_full[qs], (itq / Cfg::kQStages) & 1, p.backoff_ns));
         TR_EVT(10);
         TR_WAIT(tr_kv_full, mbar_wait(&k_full[st], (gq >> 1) & 1));
         TR_WAIT(tr_s_empty, mbar_wait(s_empty, (gq & 1) ^ 1));  // softmax has read S of the previous tile
@@ -261,7 +272,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         umma_commit(s_full);
         umma_commit(&k_empty[st]);               // K slot reusable once this QK^T has retired
-        if (jq == nkv - 1) umma_commit(q_empty);  // ... and so is Q after the item's last QK^T
+        if (jq == nkv - 1) umma_commit(&q_empty[qs]);  // ... and so is this Q buffer after the item's last QK^T
         TR_EVT(12);
       };
       if (total_tiles > 0) issue_qk(0, 0, 0);
