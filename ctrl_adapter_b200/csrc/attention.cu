@@ -21,7 +21,12 @@
 //                row's max grew by more than 2^8 since the max in use (exact: softmax is shift invariant and exp2
 //                arguments stay <= 8), so the common path never touches O.
 // The softmax warps are the bottleneck (the tensor pipe idles ~70%), so their instruction stream is what is optimised:
-//   * packed fp32x2 FFMA2 / FADD2 for the scale-and-shift and the row sum;
+//   * packed fp32x2 FFMA2 / FADD2 for the scale-and-shift and the row sum (half-rate instructions -- 2 clk of the FMA
+//     pipe each, scripts/ubench/pipes.cu -- so they save issue slots, not pipe time);
+//   * the exp schedule is THROTTLED (template TH): without it ptxas starts every long FMA-pipe chain first and leaves ~50
+//     MUFU.EX2 back to back at the end of a tile, during which the warp issues nothing else; routing each group's
+//     shift constant through fma(row_sum_of_group_g-2, 0, shift) -- numerically a no-op, but a true dependency -- keeps
+//     the MUFUs within two groups of their FMA work (783 -> 815 TFLOP/s at 16k x 16k, d = 64);
 //   * MUFU.EX2 (16 / clk / SM) is the scarcest pipe: a compile-time share of the exponentials (kPolyOf8 pairs out of
 //     8) is evaluated on the FMA pipe instead -- Cody-Waite split, cubic minimax 2^f on [-0.5, 0.5] (7.5e-5 relative,
 //     1/26 of a bf16 half-ulp of P), exponent spliced in with an integer add;
@@ -39,6 +44,7 @@
 
 namespace ca {
 
+static constexpr int kThrottleDefault = 4;  // round-2 A/B (profiles/r2_experiments.md): 783 -> 815 TFLOP/s at 16k x 16k
 static constexpr int kSplitDefault = 1;  // softmax warpgroups per CTA (column halves of a score row) for head dim 64
 static constexpr int kPolyDefault = 2;  // pairs out of every 8 whose exp2 runs on the FMA pipe instead of MUFU
 static constexpr int kTileQ = 128;
@@ -114,7 +120,7 @@ __device__ __forceinline__ void pair_bar_sync(int q) {
   }
 }
 
-template <int DQ, int POLY, int NS>
+template <int DQ, int POLY, int NS, int TH>
 __global__ void __launch_bounds__(128 + 128 * NS, (DQ == 1) ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -346,12 +352,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // The scores are read from tensor memory TWICE (max pass, exp pass) instead of being held in registers across
       // both: a tcgen05.ld of 32 columns costs a few issue cycles, while 64-128 live score registers per thread are what
       // limits the number of softmax warps an SM can hold (the register file, not the MUFU pipe, is the scarce resource).
+      // NS == 1 has the registers (208) to keep the whole row: ONE read, and the S buffer is released right away so the
+      // next tile's QK^T overlaps all of this tile's softmax.  NS == 2 (96 registers) re-reads the scores in pass 2.
+      constexpr bool kTwoPass = (NS == 2);
       float m_tile;
+      uint32_t sv[kChunks][32];
       {
-        uint32_t sv[kChunks][32];
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) tmem_ld_32x32(tmem_s + lane_sel + s_col + c * 32, sv[c]);
         TR_WAIT(tr_ld, tmem_ld_wait());
+        if constexpr (!kTwoPass) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the next QK^T may overwrite the TMEM buffer
+        }
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int c = 0; c < kChunks; ++c) {
@@ -407,33 +421,47 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // ---- pass 2: p = exp2(s*sl2 - m_used*sl2) (<= 2^8), row sum, bf16 P, 32 columns at a time ----
       const float mneg = -m_used * sl2;
       const uint64_t sl2_2 = pack_f32x2(sl2, sl2), mneg_2 = pack_f32x2(mneg, mneg);
-      uint64_t rs = pack_f32x2(0.f, 0.f);
-      uint32_t pw[kChunks][16];  // packed bf16 P of the whole row (half): kept until the previous PV has released P
+      // Row sum in three rotating accumulators.  TH > 0 ("throttle"): the scale-and-shift constant of every group of TH
+      // column pairs is routed through  fma(rs_of_group_g-2, 0, mneg)  -- numerically mneg, but a TRUE dependency on the
+      // exponentials of two groups earlier.  ptxas otherwise starts all the long FMA-pipe chains first and leaves ~50
+      // MUFU.EX2 back to back at the end of the tile (profiles/r2_ncu_attn4k_base.md: 22 % of the softmax time), during
+      // which this warp can issue nothing else; the dependency keeps the MUFUs within two groups of their FMA work.
+      uint64_t rs3[3] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+      const uint64_t zero2 = pack_f32x2(0.f, 0.f);
+      // packed bf16 P overwrites the already consumed scores in place (sv[c][0..15]) and is kept there until the previous
+      // PV has released the P buffer in tensor memory
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
         if (MASK && c >= nch) {
-          if (c == kChunks - 1) {  // the S buffer is released by the last chunk's turn even when that chunk is empty
+          if (kTwoPass && c == kChunks - 1) {  // the S buffer is released by the last chunk's turn even when it is empty
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty);
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pw[c][i] = 0u;  // P = 0 for keys that do not exist
+          for (int i = 0; i < 16; ++i) sv[c][i] = 0u;  // P = 0 for keys that do not exist
         } else {
-          uint32_t sc[32];
-          tmem_ld_32x32(tmem_s + lane_sel + s_col + c * 32, sc);
-          tmem_ld_wait();
-          if (c == kChunks - 1) {  // every score of the tile has been read for the last time: the next QK^T may start
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty);
+          uint32_t (&sc)[32] = sv[c];
+          if constexpr (kTwoPass) {
+            tmem_ld_32x32(tmem_s + lane_sel + s_col + c * 32, sc);
+            tmem_ld_wait();
+            if (c == kChunks - 1) {  // every score of the tile has been read for the last time: the next QK^T may start
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(s_empty);
+            }
           }
-          const int lim = my_valid - c * 32;
+          const int lim = my_valid - c * 32;  // valid columns of this chunk (warp-uniform; >= 32 except in the boundary chunk)
+          uint64_t mn = mneg_2;
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
+            constexpr int kGroup = TH > 0 ? TH : 16;
+            const int pair = c * 16 + (i >> 1);
+            const int grp = pair / kGroup;
+            if (TH > 0 && pair % kGroup == 0 && grp >= 2) mn = fma_f32x2(rs3[(grp + 1) % 3], zero2, mneg_2);
             const float s0 = (!MASK || i < lim) ? __uint_as_float(sc[i]) : -INFINITY;
             const float s1 = (!MASK || i + 1 < lim) ? __uint_as_float(sc[i + 1]) : -INFINITY;
-            const uint64_t x = fma_f32x2(pack_f32x2(s0, s1), sl2_2, mneg_2);
+            const uint64_t x = fma_f32x2(pack_f32x2(s0, s1), sl2_2, mn);
             float x0, x1, p0, p1;
             unpack_f32x2(x, x0, x1);
             if (pair_uses_poly<POLY>(i >> 1)) {
@@ -442,14 +470,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               p0 = fast_exp2(x0);
               p1 = fast_exp2(x1);
             }
-            rs = add_f32x2(rs, pack_f32x2(p0, p1));
-            pw[c][i >> 1] = pack_bf16x2(p0, p1);
+            rs3[grp % 3] = add_f32x2(rs3[grp % 3], pack_f32x2(p0, p1));
+            sc[i >> 1] = pack_bf16x2(p0, p1);
           }
         }
       }
       {
         float rs0, rs1;
-        unpack_f32x2(rs, rs0, rs1);
+        unpack_f32x2(add_f32x2(add_f32x2(rs3[0], rs3[1]), rs3[2]), rs0, rs1);
         l_run += rs0 + rs1;
       }
       if (tr_me) TR_EVT(22);
@@ -461,7 +489,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
       // P goes to tensor memory (the PV MMA reads its A operand from there): no shared-memory stores, no proxy fence
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) tmem_st_32x16(tmem_p + lane_sel + p_cell + c * 16, pw[c]);
+      for (int c = 0; c < kChunks; ++c)
+        tmem_st_32x16(tmem_p + lane_sel + p_cell + c * 16, *reinterpret_cast<const uint32_t(*)[16]>(&sv[c][0]));
       tmem_st_wait();
       tc_fence_before();         // orders the tcgen05.st (P, and O of a rescale) before the MMA that follows the barrier
       __syncwarp();
@@ -531,16 +560,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
-template <int DQ, int POLY, int NS>
+template <int DQ, int POLY, int NS, int TH = 0>
 static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream) {
   using Cfg = AttnCfg<DQ>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, NS, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(Cfg::kSmemBytes));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, NS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    e = cudaFuncSetAttribute(attention_kernel<DQ, POLY, NS, TH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -558,7 +587,7 @@ static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const C
   // developer knobs: CA_ATTN_GRID=items launches one CTA per work item (hardware block scheduler, dynamic balance)
   static const bool per_item = getenv("CA_ATTN_GRID") && getenv("CA_ATTN_GRID")[0] == 'i';
   const int grid = static_cast<int>((items < resident || per_item) ? items : resident);
-  auto kern = attention_kernel<DQ, POLY, NS>;
+  auto kern = attention_kernel<DQ, POLY, NS, TH>;
   CA_KERNEL_LAUNCH(kern, grid, 128 + 128 * NS, Cfg::kSmemBytes, stream, q, k, v, p);
   return cudaGetLastError();
 }
@@ -569,9 +598,16 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
   // CA_ATTN_POLY = share of exponentials moved off the MUFU pipe (eighths)
   static const int split = getenv("CA_ATTN_SPLIT") ? atoi(getenv("CA_ATTN_SPLIT")) : kSplitDefault;
   static const int poly = getenv("CA_ATTN_POLY") ? atoi(getenv("CA_ATTN_POLY")) : kPolyDefault;
+  // CA_ATTN_THROTTLE = column pairs per dependency group of the exp schedule throttle (0 = off; 4 or 8)
+  static const int th = getenv("CA_ATTN_THROTTLE") ? atoi(getenv("CA_ATTN_THROTTLE")) : kThrottleDefault;
   switch (p.dqk_chunks) {
     case 1:
-      if (split == 1) return launch_dq<1, kPolyDefault, 1>(q, k, v, p, stream);
+      if (split == 1) {
+        if (th == 2) return poly == 3 ? launch_dq<1, 3, 1, 2>(q, k, v, p, stream) : launch_dq<1, kPolyDefault, 1, 2>(q, k, v, p, stream);
+        if (th == 4) return poly == 3 ? launch_dq<1, 3, 1, 4>(q, k, v, p, stream) : launch_dq<1, kPolyDefault, 1, 4>(q, k, v, p, stream);
+        if (th == 8) return poly == 3 ? launch_dq<1, 3, 1, 8>(q, k, v, p, stream) : launch_dq<1, kPolyDefault, 1, 8>(q, k, v, p, stream);
+        return launch_dq<1, kPolyDefault, 1>(q, k, v, p, stream);
+      }
       switch (poly) {
         case 0: return launch_dq<1, 0, 2>(q, k, v, p, stream);
         case 3: return launch_dq<1, 3, 2>(q, k, v, p, stream);
