@@ -136,7 +136,12 @@ int ca_gemm(const ca_gemm_desc* d, void* cuda_stream) {
   // (kernel checks green on hardware, 181.8 -> 179.7 ms / SDXL step); CA_GEMM_BN320=0 restores the 160-wide tiles.
   static const bool wide_ok = !(getenv("CA_GEMM_BN320") && getenv("CA_GEMM_BN320")[0] == '0') &&
                               getenv("CA_GEMM_1CTA") == nullptr;
-  if (wide_ok && d->bn == 0 && bn == 160 && d->w_rows % 320 == 0 && d->act == CA_ACT_NONE && !d->out_fp32 &&
+  // ... and only for long contractions: its two-half tiles pay off from ~24 k-blocks on (3x3 convolutions, K >= 1920
+  // linears: +5..9 %); for the thin GEMMs of the video backbones (K = 320 .. 1280) the 160-wide kernel is 4..60 % faster
+  // (profiles/r2_experiments.md, "BN = 320 dispatch threshold")
+  const long long k_total = static_cast<long long>(d->ntaps) * d->w_k_per_tap;
+  static const long long wide_min_k = getenv("CA_GEMM_BN320_MINK") ? atoll(getenv("CA_GEMM_BN320_MINK")) : 1536;  // A/B knob
+  if (wide_ok && k_total >= wide_min_k && d->bn == 0 && bn == 160 && d->w_rows % 320 == 0 && d->act == CA_ACT_NONE && !d->out_fp32 &&
       d->out_scale == 1.0f && d->blend_src == nullptr && (d->rowvec == nullptr || d->residual == nullptr) &&
       reinterpret_cast<uintptr_t>(d->bias) % 16 == 0)
     bn = 320;

@@ -67,6 +67,19 @@ def main():
         "geglu 16384x1280->10240": (lin(16384, 1280, 10240, act=ops.ACT_GEGLU), 2.0 * 16384 * 1280 * 10240),
         "geglu 65536x640->5120": (lin(65536, 640, 5120, act=ops.ACT_GEGLU), 2.0 * 65536 * 640 * 5120),
         "conv3 16x128x128 320->320": (conv(16, 128, 320, 320), 2.0 * 16 * 128 * 128 * 2880 * 320),
+        # thin (small K, small N) GEMMs of the video backbones: HBM-bound by their operands, far from it in round 2
+        "thin 524288x320->320 +res": (lin(524288, 320, 320, res=True), 2.0 * 524288 * 320 * 320),
+        "thin 524288x320->320": (lin(524288, 320, 320), 2.0 * 524288 * 320 * 320),
+        "thin 524288x320->960": (lin(524288, 320, 960), 2.0 * 524288 * 320 * 960),
+        "thin 131072x640->640 +res": (lin(131072, 640, 640, res=True), 2.0 * 131072 * 640 * 640),
+        "thin 524288x512->320 +res": (lin(524288, 512, 320, res=True), 2.0 * 524288 * 512 * 320),
+        "mid 524288x1280->320 +res": (lin(524288, 1280, 320, res=True), 2.0 * 524288 * 1280 * 320),
+        "mid 131072x2560->640 +res": (lin(131072, 2560, 640, res=True), 2.0 * 131072 * 2560 * 640),
+        "mid 65536x640->1920": (lin(65536, 640, 1920), 2.0 * 65536 * 640 * 1920),
+        "mid 131072x1024->640": (lin(131072, 1024, 640), 2.0 * 131072 * 1024 * 640),
+        "mid 65536x1920->640": (lin(65536, 1920, 640), 2.0 * 65536 * 1920 * 640),
+        "mid conv3 16x64x64 320->320": (conv(16, 64, 320, 320), 2.0 * 16 * 64 * 64 * 2880 * 320),
+        "mid conv3 128x64x64 320->320": (conv(128, 64, 320, 320), 2.0 * 128 * 64 * 64 * 2880 * 320),
     }
     def attn(b, h, l, lk=None):
         qkv = rnd(b, l, 3 * h * 64)
