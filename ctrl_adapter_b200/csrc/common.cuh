@@ -121,6 +121,15 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` is a multiple of 16, both addresses 16-byte aligned; the
+// copy completes `bytes` of transaction count on `bar`
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------
 // TMA (bulk tensor copies, tile mode).  The tensor map lives in kernel param
 // space (__grid_constant__), so its generic address can be used directly.

@@ -247,131 +247,217 @@ cudaError_t launch_gn_apply(const __nv_bfloat16* x0, int c0, const __nv_bfloat16
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, the row is held in registers (NV 16-byte vectors per lane): one global read,
-// two-pass mean / variance from registers, one write.  The kernel is instruction-issue bound next to the HBM rate
-// (40 elements per lane at C = 1280), so the arithmetic runs on packed fp32x2 (FADD2 / FFMA2 / FMUL2).
+// LayerNorm: one warp per row, rows walked with a grid-wide stride by resident warps.
+//  * Each warp owns a three-row ring in shared memory that one lane fills with 1-D bulk copies (cp.async.bulk +
+//    mbarrier): the next rows are in flight while the warp works, at no register cost.
+//  * The row is NOT held in registers: each of the three passes (sum, centred sum of squares, normalise) re-reads its
+//    16-byte vectors from the stage.  The registers hold gamma and beta instead (16 x NV per lane, the lane's columns
+//    are the same for every row).  The first bulk-copy version still loaded them per row and ran at the L1 rate:
+//    8 bytes of fp32 gamma / beta per 2-byte element, l1tex throughput 72 % (profiles/r2_layernorm_ab.md).
+//  * Arithmetic on packed fp32x2 (FADD2 / FFMA2 / FMUL2).
 // RV: fused pre-add of a broadcast row vector (frame position embedding / single-token cross-attention output),
-// rounded to bf16 like the eager add it replaces; optionally also written out (y_sum).
+// rounded to bf16 like the eager add it replaces, written back into the stage; optionally also written out (y_sum).
 // ---------------------------------------------------------------------------------------------
+constexpr int kLnWarps = 8;
+constexpr int kLnStages = 3;
+constexpr int kLnRingMaxBytes = kLnWarps * kLnStages * (2048 * 2 + 8);  // widest row the launcher accepts
+constexpr int kLnHoldMaxNV = 5;  // C <= 1280: gamma / beta stay in registers; wider rows reload them per row
+__host__ __device__ constexpr int ln_blocks_per_sm(int nv) { return nv <= 3 ? 3 : (nv <= kLnHoldMaxNV ? 2 : 3); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {  // volatile: the three passes must not be merged into registers
+  uint4 q;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(saddr));
+  return q;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& q) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w)
+               : "memory");
+}
+
 template <int NV, bool RV>
-__global__ void __launch_bounds__(256, (NV <= 5) ? 5 : 3)
+__global__ void __launch_bounds__(kLnWarps * 32, ln_blocks_per_sm(NV))
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, float eps,
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  const __nv_bfloat16* __restrict__ add_rowvec, long long rows_per_vec,
                  __nv_bfloat16* __restrict__ y_sum, __nv_bfloat16* __restrict__ y) {
-  CA_PDL_TRIGGER();
-  CA_PDL_WAIT();
-  const int warps_per_block = blockDim.x >> 5;
+  constexpr bool kHold = NV <= kLnHoldMaxNV;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = c >> 3;
-  // resident warps walk the rows with a grid-wide stride (round 2): one-row-per-warp blocks lived ~1.5 us each and the
-  // SM spent half of the time re-filling its block slots (warps active 52 % in profiles/r1_ncu_ln.md)
-  const long long row_stride = static_cast<long long>(gridDim.x) * warps_per_block;
-  for (long long row = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5); row < rows;
-       row += row_stride) {
-  const __nv_bfloat16* xr = x + row * c;
-  [[maybe_unused]] const __nv_bfloat16* av = RV ? add_rowvec + (row / rows_per_vec) * c : nullptr;
-  uint4 u[NV];
+  const uint32_t row_bytes = static_cast<uint32_t>(c) * 2u;
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * kLnStages * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(kLnWarps) * kLnStages * row_bytes) +
+                   warp * kLnStages;
+  if (lane == 0) {
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nvec) u[k] = ld_nc(xr + v * 8);
+    for (int s = 0; s < kLnStages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
   }
-  // The row stays PACKED (bf16 pairs, NV*4 registers) and is widened again in each of the three passes: the kernel
-  // is bound by bytes in flight per SM, i.e. by occupancy, so registers are worth more than the extra shifts.
+  __syncwarp();
+  auto load_gb = [&](int k, uint64_t (&g)[4], uint64_t (&b)[4]) {
+    const int v = lane + 32 * k;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+    g[0] = pack_f32x2(g0.x, g0.y); g[1] = pack_f32x2(g0.z, g0.w); g[2] = pack_f32x2(g1.x, g1.y); g[3] = pack_f32x2(g1.z, g1.w);
+    b[0] = pack_f32x2(b0.x, b0.y); b[1] = pack_f32x2(b0.z, b0.w); b[2] = pack_f32x2(b1.x, b1.y); b[3] = pack_f32x2(b1.z, b1.w);
+  };
+  // parameters, not produced by the previous kernel: loaded ahead of the programmatic-launch wait
+  [[maybe_unused]] uint64_t gg[kHold ? NV : 1][4], bb[kHold ? NV : 1][4];
+  if constexpr (kHold) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) gg[k][e] = bb[k][e] = 0;
+      if (lane + 32 * k < nvec) load_gb(k, gg[k], bb[k]);
+    }
+  }
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
+  const long long row_stride = static_cast<long long>(gridDim.x) * kLnWarps;
+  const long long row0 = static_cast<long long>(blockIdx.x) * kLnWarps + warp;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kLnStages; ++s) {
+      const long long r = row0 + s * row_stride;
+      if (r < rows) {
+        mbar_arrive_expect_tx(&bars[s], row_bytes);
+        bulk_load_1d(ring + s * row_bytes, x + r * c, row_bytes, &bars[s]);
+      }
+    }
+  }
   auto widen = [](uint32_t w) { return pack_f32x2(bf16lo_to_float(w), bf16hi_to_float(w)); };
-  uint64_t s2 = pack_f32x2(0.f, 0.f);
+  uint32_t stage = 0, phase = 0;
+  for (long long row = row0; row < rows; row += row_stride) {
+    [[maybe_unused]] const __nv_bfloat16* av = RV ? add_rowvec + (row / rows_per_vec) * c : nullptr;
+    const uint32_t srow = smem_u32(ring + stage * row_bytes) + lane * 16;  // this lane's vector k is at srow + 512 k
+    mbar_wait(&bars[stage], phase);
+    // pass 1: sum (and the fused row-vector add)
+    uint64_t s2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nvec) {
-      if constexpr (RV) {
-        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(av + v * 8));
-        u[k].x = add_bf16x2(u[k].x, ua.x);  // bf16(x + rowvec), one rounding
-        u[k].y = add_bf16x2(u[k].y, ua.y);
-        u[k].z = add_bf16x2(u[k].z, ua.z);
-        u[k].w = add_bf16x2(u[k].w, ua.w);
-        if (y_sum) *reinterpret_cast<uint4*>(y_sum + row * c + v * 8) = u[k];
-      }
-      s2 = add_f32x2(add_f32x2(s2, widen(u[k].x)), widen(u[k].y));
-      s2 = add_f32x2(add_f32x2(s2, widen(u[k].z)), widen(u[k].w));
-    }
-  }
-  float s_lo, s_hi;
-  unpack_f32x2(s2, s_lo, s_hi);
-  float s = s_lo + s_hi;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / c;
-  const uint64_t nmean2 = pack_f32x2(-mean, -mean);
-  uint64_t ss2 = pack_f32x2(0.f, 0.f);
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    if (lane + 32 * k < nvec) {
-      const uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint64_t d = add_f32x2(widen(wds[e]), nmean2);
-        ss2 = fma_f32x2(d, d, ss2);
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        uint4 q = lds128(srow + 512 * k);
+        if constexpr (RV) {
+          const uint4 ua = __ldg(reinterpret_cast<const uint4*>(av + v * 8));
+          q.x = add_bf16x2(q.x, ua.x);  // bf16(x + rowvec), one rounding
+          q.y = add_bf16x2(q.y, ua.y);
+          q.z = add_bf16x2(q.z, ua.z);
+          q.w = add_bf16x2(q.w, ua.w);
+          sts128(srow + 512 * k, q);    // passes 2 and 3 of this lane read it back
+          if (y_sum) *reinterpret_cast<uint4*>(y_sum + row * c + v * 8) = q;
+        }
+        s2 = add_f32x2(add_f32x2(s2, widen(q.x)), widen(q.y));
+        s2 = add_f32x2(add_f32x2(s2, widen(q.z)), widen(q.w));
       }
     }
-  }
-  float ss_lo, ss_hi;
-  unpack_f32x2(ss2, ss_lo, ss_hi);
-  float ss = ss_lo + ss_hi;
+    float s_lo, s_hi;
+    unpack_f32x2(s2, s_lo, s_hi);
+    float s = s_lo + s_hi;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss / c + eps);
-  const uint64_t rstd2 = pack_f32x2(rstd, rstd);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / c;
+    const uint64_t nmean2 = pack_f32x2(-mean, -mean);
+    // pass 2: centred sum of squares
+    uint64_t ss2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int v = lane + 32 * k;
-    if (v < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
-      const uint64_t gg[4] = {pack_f32x2(g0.x, g0.y), pack_f32x2(g0.z, g0.w), pack_f32x2(g1.x, g1.y),
-                              pack_f32x2(g1.z, g1.w)};
-      const uint64_t bb[4] = {pack_f32x2(b0.x, b0.y), pack_f32x2(b0.z, b0.w), pack_f32x2(b1.x, b1.y),
-                              pack_f32x2(b1.z, b1.w)};
-      const uint32_t wds[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-      uint32_t o[4];
+    for (int k = 0; k < NV; ++k) {
+      if (lane + 32 * k < nvec) {
+        const uint4 q = lds128(srow + 512 * k);
+        const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        // ((x - mean) * rstd) * gamma + beta, the association of the eager kernel
-        const uint64_t r = fma_f32x2(mul_f32x2(add_f32x2(widen(wds[e]), nmean2), rstd2), gg[e], bb[e]);
-        float r0, r1;
-        unpack_f32x2(r, r0, r1);
-        o[e] = pack_bf16x2(r0, r1);
+        for (int e = 0; e < 4; ++e) {
+          const uint64_t d = add_f32x2(widen(wds[e]), nmean2);
+          ss2 = fma_f32x2(d, d, ss2);
+        }
       }
-      *reinterpret_cast<uint4*>(y + row * c + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    float ss_lo, ss_hi;
+    unpack_f32x2(ss2, ss_lo, ss_hi);
+    float ss = ss_lo + ss_hi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / c + eps);
+    const uint64_t rstd2 = pack_f32x2(rstd, rstd);
+    // pass 3: normalise, scale, shift, store
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        const uint4 q = lds128(srow + 512 * k);
+        const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+        [[maybe_unused]] uint64_t g1[4], b1[4];
+        if constexpr (!kHold) load_gb(k, g1, b1);
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint64_t ge = kHold ? gg[kHold ? k : 0][e] : g1[e];
+          const uint64_t be = kHold ? bb[kHold ? k : 0][e] : b1[e];
+          // ((x - mean) * rstd) * gamma + beta, the association of the eager kernel
+          const uint64_t r = fma_f32x2(mul_f32x2(add_f32x2(widen(wds[e]), nmean2), rstd2), ge, be);
+          float r0, r1;
+          unpack_f32x2(r, r0, r1);
+          o[e] = pack_bf16x2(r0, r1);
+        }
+        *reinterpret_cast<uint4*>(y + row * c + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncwarp();  // every lane is done with the stage: refill it with the row kLnStages ahead
+    if (lane == 0) {
+      const long long r = row + kLnStages * row_stride;
+      if (r < rows) {
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx(&bars[stage], row_bytes);
+        bulk_load_1d(ring + stage * row_bytes, x + r * c, row_bytes, &bars[stage]);
+      }
+    }
+    if (++stage == kLnStages) {
+      stage = 0;
+      phase ^= 1u;
     }
   }
-  }  // row loop
 }
 
 cudaError_t launch_layernorm(const __nv_bfloat16* x, long long rows, int c, float eps, const float* gamma,
                              const float* beta, const __nv_bfloat16* add_rowvec, long long rows_per_vec,
                              __nv_bfloat16* y_sum, __nv_bfloat16* y, cudaStream_t stream) {
   if ((c & 7) != 0 || c > 8 * 32 * 8) return cudaErrorInvalidValue;
-  const int warps = 8;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorMisalignedAddress;  // bulk copies of whole rows
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
   }
-  const int nv0 = ((c >> 3) + 31) / 32;
-  const long long resident = static_cast<long long>(sms) * (nv0 <= 5 ? 5 : 3);  // matches the kernel's launch bounds
-  const long long need = (rows + warps - 1) / warps;
+  const int nv = ((c >> 3) + 31) / 32;
+  const size_t smem = static_cast<size_t>(kLnWarps) * kLnStages * (static_cast<size_t>(c) * 2 + sizeof(uint64_t));
+  // blocks that fit one SM: the launch bound or the shared-memory ring (228 KB per SM, 1 KB reserved per block)
+  int per_sm = ln_blocks_per_sm(nv);
+  const int by_smem = static_cast<int>((228u * 1024u) / (smem + 1024u));
+  if (by_smem < per_sm) per_sm = by_smem;
+  const long long resident = static_cast<long long>(sms) * per_sm;
+  const long long need = (rows + kLnWarps - 1) / kLnWarps;
   const unsigned blocks = static_cast<unsigned>(need < resident ? need : resident);
   const long long rpv = rows_per_vec > 0 ? rows_per_vec : 1;
-  const int nv = ((c >> 3) + 31) / 32;
 #define CA_LN(NV)                                                                                                      \
   do {                                                                                                                 \
+    static bool optin = false; /* the ring can exceed the 48 KB default: opt both variants in once */                  \
+    if (!optin) {                                                                                                      \
+      cudaError_t e = cudaFuncSetAttribute(layernorm_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                           kLnRingMaxBytes);                                                           \
+      if (e == cudaSuccess)                                                                                            \
+        e = cudaFuncSetAttribute(layernorm_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                 kLnRingMaxBytes);                                                                     \
+      if (e != cudaSuccess) return e;                                                                                  \
+      optin = true;                                                                                                    \
+    }                                                                                                                  \
     auto kern = (add_rowvec != nullptr) ? layernorm_kernel<NV, true> : layernorm_kernel<NV, false>;                   \
-    CA_KERNEL_LAUNCH(kern, blocks, warps * 32, 0, stream, x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y);    \
+    CA_KERNEL_LAUNCH(kern, blocks, kLnWarps * 32, smem, stream, x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum,  \
+                     y);                                                                                               \
   } while (0)
   switch (nv) {
     case 1: CA_LN(1); break;

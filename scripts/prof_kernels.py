@@ -58,11 +58,17 @@ elif which.startswith("tattn"):  # temporal attention at config 3's adapter-A sh
                                         heads, 0.125, row_stride=3 * inner)
     flops = 4.0 * clips * hw * heads * frames * frames * 64
     nbytes = 4.0 * clips * frames * hw * inner * 2
-elif which == "ln":
-    x = rnd(16384, 1280)
-    g, b = torch.ones(1280, device=dev), torch.zeros(1280, device=dev)
-    fn = lambda: ops.layer_norm(x, g, b)  # noqa: E731
+elif which in ("ln", "ln640", "ln320"):
+    rows, c = {"ln": (16384, 1280), "ln640": (65536, 640), "ln320": (131072, 320)}[which]
+    xs = [rnd(rows, c) for _ in range(8)]   # 8 x 42 MB rotate through the 126 MB L2: every launch reads from HBM
+    g, b = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    _i = [0]
+
+    def fn():
+        _i[0] += 1
+        return ops.layer_norm(xs[_i[0] % 8], g, b)
     flops = 0.0
+    nbytes = 2.0 * rows * c * 2
 elif which == "gn":
     x = rnd(16, 128, 128, 320)
     g, b = torch.ones(320, device=dev), torch.zeros(320, device=dev)
@@ -83,5 +89,5 @@ if do_time:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    extra = f"  {nbytes / ms / 1e6:.0f} GB/s" if which.startswith("tattn") else ""
+    extra = f"  {nbytes / ms / 1e6:.0f} GB/s" if which.startswith(("tattn", "ln")) else ""
     print(f"{which}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s{extra}")

@@ -453,6 +453,12 @@ def run_all(stop_on_fail=False, group=None):
         lambda: check_layernorm(1000, 512),
         lambda: check_layernorm(400, 320, add=True),
         lambda: check_layernorm(64, 1280),
+        # more rows than resident warps: every warp walks several rows through its two-stage bulk-copy ring
+        lambda: check_layernorm(30001, 1280),
+        lambda: check_layernorm(70000, 640),
+        lambda: check_layernorm(40000, 320, add=True),
+        lambda: check_layernorm(9000, 2048),     # 64 KB ring per block (opt-in shared memory)
+        lambda: check_layernorm(5, 8),
         lambda: check_softmax_rows(300, 4096),
         lambda: check_softmax_rows(64, 16384),
         check_timestep_embedding,
