@@ -247,24 +247,30 @@ cudaError_t launch_gn_apply(const __nv_bfloat16* x0, int c0, const __nv_bfloat16
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, rows walked with a grid-wide stride by resident warps.
-//  * Each warp owns a three-row ring in shared memory that one lane fills with 1-D bulk copies (cp.async.bulk +
-//    mbarrier): the next rows are in flight while the warp works, at no register cost.
-//  * The row is NOT held in registers: each of the three passes (sum, centred sum of squares, normalise) re-reads its
-//    16-byte vectors from the stage.  The registers hold gamma and beta instead (16 x NV per lane, the lane's columns
-//    are the same for every row).  The first bulk-copy version still loaded them per row and ran at the L1 rate:
-//    8 bytes of fp32 gamma / beta per 2-byte element, l1tex throughput 72 % (profiles/r2_layernorm_ab.md).
+// LayerNorm.  A group of L lanes (8, 16 or 32) normalises one row, so a warp works on G = 32 / L consecutive rows at a
+// time and every lane owns NV = ceil(C / 8 / L) 16-byte vectors of its row: C = 320 / 640 / 1280 all map to NV = 5
+// with no idle lanes (L = 8 / 16 / 32).  Resident warps walk the G-row steps with a grid-wide stride.
+//  * Each warp owns a three-step ring in shared memory that one lane fills with 1-D bulk copies (cp.async.bulk +
+//    mbarrier; the G rows of a step are contiguous in memory): the next steps are in flight while the warp works, at
+//    no register cost.
+//  * The rows are NOT held in registers: both passes re-read their vectors from the stage.  The registers hold gamma
+//    and beta instead (16 x NV per lane; a lane's columns are the same for every row).  Loading them per row ran the
+//    kernel at the L1 rate: 8 bytes of fp32 gamma / beta per 2-byte element (profiles/r2_layernorm_ab.md).
+//  * Statistics in ONE pass over d = x - K with K = the row's first element: mean = K + sum(d)/C,
+//    var = (sum(d^2) - sum(d)^2 / C) / C.  K is an element of the row, so (K - mean)^2 <= (C - 1) var and the
+//    cancellation costs at most ~C ulp of fp32 in var (1.5e-4 relative at C = 1280), far below the bf16 output grid.
 //  * Arithmetic on packed fp32x2 (FADD2 / FFMA2 / FMUL2).
 // RV: fused pre-add of a broadcast row vector (frame position embedding / single-token cross-attention output),
 // rounded to bf16 like the eager add it replaces, written back into the stage; optionally also written out (y_sum).
 // ---------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 8;
 constexpr int kLnStages = 3;
-constexpr int kLnRingMaxBytes = kLnWarps * kLnStages * (2048 * 2 + 8);  // widest row the launcher accepts
-constexpr int kLnHoldMaxNV = 5;  // C <= 1280: gamma / beta stay in registers; wider rows reload them per row
-__host__ __device__ constexpr int ln_blocks_per_sm(int nv) { return nv <= 3 ? 3 : (nv <= kLnHoldMaxNV ? 2 : 3); }
+constexpr int kLnHoldMaxNV = 5;   // gamma / beta stay in registers up to 5 vectors per lane; wider rows reload them
+constexpr int kLnMaxC = 8 * 32 * 8;
+constexpr int kLnRingMaxBytes = kLnWarps * kLnStages * (kLnMaxC * 2 + 8);  // widest step the launcher builds
+__host__ __device__ constexpr int ln_blocks_per_sm(int nv) { return nv <= 2 ? 3 : (nv <= kLnHoldMaxNV ? 2 : 3); }
 
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {  // volatile: the three passes must not be merged into registers
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {  // volatile: the passes must not be merged into registers
   uint4 q;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(saddr));
   return q;
@@ -274,20 +280,24 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& q) {
                : "memory");
 }
 
-template <int NV, bool RV>
+template <int NV, int L, bool RV>
 __global__ void __launch_bounds__(kLnWarps * 32, ln_blocks_per_sm(NV))
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, float eps,
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  const __nv_bfloat16* __restrict__ add_rowvec, long long rows_per_vec,
                  __nv_bfloat16* __restrict__ y_sum, __nv_bfloat16* __restrict__ y) {
   constexpr bool kHold = NV <= kLnHoldMaxNV;
+  constexpr int G = 32 / L;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int sub = lane / L;   // which row of the step
+  const int ll = lane % L;    // position inside the row's lane group
   const int nvec = c >> 3;
   const uint32_t row_bytes = static_cast<uint32_t>(c) * 2u;
-  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * kLnStages * row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(kLnWarps) * kLnStages * row_bytes) +
+  const uint32_t step_bytes = G * row_bytes;
+  uint8_t* ring = ln_smem + static_cast<size_t>(warp) * kLnStages * step_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(kLnWarps) * kLnStages * step_bytes) +
                    warp * kLnStages;
   if (lane == 0) {
 #pragma unroll
@@ -296,8 +306,7 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
     fence_proxy_async_smem();
   }
   __syncwarp();
-  auto load_gb = [&](int k, uint64_t (&g)[4], uint64_t (&b)[4]) {
-    const int v = lane + 32 * k;
+  auto load_gb = [&](int v, uint64_t (&g)[4], uint64_t (&b)[4]) {
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
@@ -305,6 +314,8 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
     g[0] = pack_f32x2(g0.x, g0.y); g[1] = pack_f32x2(g0.z, g0.w); g[2] = pack_f32x2(g1.x, g1.y); g[3] = pack_f32x2(g1.z, g1.w);
     b[0] = pack_f32x2(b0.x, b0.y); b[1] = pack_f32x2(b0.z, b0.w); b[2] = pack_f32x2(b1.x, b1.y); b[3] = pack_f32x2(b1.z, b1.w);
   };
+  // vector k of this lane is column block v = ll + L k; only the last k can fall off the end of the row
+  auto has = [&](int k) { return k < NV - 1 || ll + L * k < nvec; };
   // parameters, not produced by the previous kernel: loaded ahead of the programmatic-launch wait
   [[maybe_unused]] uint64_t gg[kHold ? NV : 1][4], bb[kHold ? NV : 1][4];
   if constexpr (kHold) {
@@ -312,86 +323,93 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
     for (int k = 0; k < NV; ++k) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) gg[k][e] = bb[k][e] = 0;
-      if (lane + 32 * k < nvec) load_gb(k, gg[k], bb[k]);
+      if (has(k)) load_gb(ll + L * k, gg[k], bb[k]);
     }
   }
   CA_PDL_TRIGGER();
   CA_PDL_WAIT();
-  const long long row_stride = static_cast<long long>(gridDim.x) * kLnWarps;
-  const long long row0 = static_cast<long long>(blockIdx.x) * kLnWarps + warp;
+  // step counters are 32-bit (the launcher rejects rows >= 2^31); only the element offsets need 64 bits
+  const int nrows = static_cast<int>(rows);
+  const int steps = (nrows + G - 1) / G;
+  const int step_stride = static_cast<int>(gridDim.x) * kLnWarps;
+  const int step0 = static_cast<int>(blockIdx.x) * kLnWarps + warp;
+  auto fill = [&](uint32_t stage, int step) {  // lane 0 only
+    const int r0 = step * G;
+    const int left = nrows - r0;
+    const uint32_t bytes = static_cast<uint32_t>(left < G ? left : G) * row_bytes;
+    mbar_arrive_expect_tx(&bars[stage], bytes);
+    bulk_load_1d(ring + stage * step_bytes, x + static_cast<long long>(r0) * c, bytes, &bars[stage]);
+  };
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kLnStages; ++s) {
-      const long long r = row0 + s * row_stride;
-      if (r < rows) {
-        mbar_arrive_expect_tx(&bars[s], row_bytes);
-        bulk_load_1d(ring + s * row_bytes, x + r * c, row_bytes, &bars[s]);
-      }
-    }
+    for (int s = 0; s < kLnStages; ++s)
+      if (step0 + s * step_stride < steps) fill(s, step0 + s * step_stride);
   }
   auto widen = [](uint32_t w) { return pack_f32x2(bf16lo_to_float(w), bf16hi_to_float(w)); };
+  const float inv_c = 1.f / static_cast<float>(c);
   uint32_t stage = 0, phase = 0;
-  for (long long row = row0; row < rows; row += row_stride) {
-    [[maybe_unused]] const __nv_bfloat16* av = RV ? add_rowvec + (row / rows_per_vec) * c : nullptr;
-    const uint32_t srow = smem_u32(ring + stage * row_bytes) + lane * 16;  // this lane's vector k is at srow + 512 k
+  for (int step = step0; step < steps; step += step_stride) {
+    const int row = step * G + sub;
+    const bool row_ok = row < nrows;  // a short last step leaves stale bytes in the stage: computed on, never stored
+    [[maybe_unused]] const __nv_bfloat16* av = RV ? add_rowvec + (static_cast<long long>(row_ok ? row : 0) / rows_per_vec) * c : nullptr;
+    // this lane's vector k sits at srow + 16 L k
+    const uint32_t srow = smem_u32(ring + stage * step_bytes) + sub * row_bytes + ll * 16;
     mbar_wait(&bars[stage], phase);
-    // pass 1: sum (and the fused row-vector add)
-    uint64_t s2 = pack_f32x2(0.f, 0.f);
+    // the shift K: the row's first element (after the row-vector add, when there is one)
+    uint32_t kw;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(kw) : "r"(srow - ll * 16));
+    if constexpr (RV) kw = add_bf16x2(kw, __ldg(reinterpret_cast<const uint32_t*>(av)));
+    const float shift = bf16lo_to_float(kw);
+    const uint64_t nshift2 = pack_f32x2(-shift, -shift);
+    // pass 1: sum and sum of squares of d = x - K (and the fused row-vector add)
+    uint64_t s2 = pack_f32x2(0.f, 0.f), ss2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int v = lane + 32 * k;
-      if (v < nvec) {
-        uint4 q = lds128(srow + 512 * k);
+      if (has(k)) {
+        uint4 q = lds128(srow + 16 * L * k);
         if constexpr (RV) {
+          const int v = ll + L * k;
           const uint4 ua = __ldg(reinterpret_cast<const uint4*>(av + v * 8));
           q.x = add_bf16x2(q.x, ua.x);  // bf16(x + rowvec), one rounding
           q.y = add_bf16x2(q.y, ua.y);
           q.z = add_bf16x2(q.z, ua.z);
           q.w = add_bf16x2(q.w, ua.w);
-          sts128(srow + 512 * k, q);    // passes 2 and 3 of this lane read it back
-          if (y_sum) *reinterpret_cast<uint4*>(y_sum + row * c + v * 8) = q;
+          sts128(srow + 16 * L * k, q);  // pass 2 of this lane reads it back
+          if (y_sum != nullptr && row_ok) *reinterpret_cast<uint4*>(y_sum + static_cast<long long>(row) * c + v * 8) = q;
         }
-        s2 = add_f32x2(add_f32x2(s2, widen(q.x)), widen(q.y));
-        s2 = add_f32x2(add_f32x2(s2, widen(q.z)), widen(q.w));
-      }
-    }
-    float s_lo, s_hi;
-    unpack_f32x2(s2, s_lo, s_hi);
-    float s = s_lo + s_hi;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / c;
-    const uint64_t nmean2 = pack_f32x2(-mean, -mean);
-    // pass 2: centred sum of squares
-    uint64_t ss2 = pack_f32x2(0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      if (lane + 32 * k < nvec) {
-        const uint4 q = lds128(srow + 512 * k);
         const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const uint64_t d = add_f32x2(widen(wds[e]), nmean2);
+          const uint64_t d = add_f32x2(widen(wds[e]), nshift2);
+          s2 = add_f32x2(s2, d);
           ss2 = fma_f32x2(d, d, ss2);
         }
       }
     }
-    float ss_lo, ss_hi;
+    float s_lo, s_hi, ss_lo, ss_hi;
+    unpack_f32x2(s2, s_lo, s_hi);
     unpack_f32x2(ss2, ss_lo, ss_hi);
-    float ss = ss_lo + ss_hi;
+    float sd = s_lo + s_hi, sq = ss_lo + ss_hi;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rstd = rsqrtf(ss / c + eps);
+    for (int o = L / 2; o > 0; o >>= 1) {
+      sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float mean_d = sd * inv_c;
+    const float var = fmaxf((sq - sd * mean_d) * inv_c, 0.f);
+    const float mean = shift + mean_d;
+    const float rstd = rsqrtf(var + eps);
+    const uint64_t nmean2 = pack_f32x2(-mean, -mean);
     const uint64_t rstd2 = pack_f32x2(rstd, rstd);
-    // pass 3: normalise, scale, shift, store
+    // pass 2: normalise, scale, shift, store
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int v = lane + 32 * k;
-      if (v < nvec) {
-        const uint4 q = lds128(srow + 512 * k);
+      if (has(k)) {
+        const int v = ll + L * k;
+        const uint4 q = lds128(srow + 16 * L * k);
         const uint32_t wds[4] = {q.x, q.y, q.z, q.w};
         [[maybe_unused]] uint64_t g1[4], b1[4];
-        if constexpr (!kHold) load_gb(k, g1, b1);
+        if constexpr (!kHold) load_gb(v, g1, b1);
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -403,17 +421,16 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
           unpack_f32x2(r, r0, r1);
           o[e] = pack_bf16x2(r0, r1);
         }
-        *reinterpret_cast<uint4*>(y + row * c + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        if (row_ok) *reinterpret_cast<uint4*>(y + static_cast<long long>(row) * c + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
-    __syncwarp();  // every lane is done with the stage: refill it with the row kLnStages ahead
+    __syncwarp();  // every lane is done with the stage: refill it with the step kLnStages ahead
     if (lane == 0) {
-      const long long r = row + kLnStages * row_stride;
-      if (r < rows) {
-        fence_proxy_async_smem();
-        mbar_arrive_expect_tx(&bars[stage], row_bytes);
-        bulk_load_1d(ring + stage * row_bytes, x + r * c, row_bytes, &bars[stage]);
-      }
+      const int nxt = step + kLnStages * step_stride;
+      // no proxy fence: every lane has consumed what it read from (or, RV, wrote to and read back from) the stage
+      // before the __syncwarp above, the same release convention as the TMA rings of the GEMM kernels; a fence here
+      // is a MEMBAR that also waits for this lane's row stores
+      if (nxt < steps) fill(stage, nxt);
     }
     if (++stage == kLnStages) {
       stage = 0;
@@ -422,55 +439,84 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int c, flo
   }
 }
 
+namespace {
+template <int NV, int L>
+cudaError_t launch_layernorm_t(const __nv_bfloat16* x, long long rows, int c, float eps, const float* gamma,
+                               const float* beta, const __nv_bfloat16* add_rowvec, long long rpv, __nv_bfloat16* y_sum,
+                               __nv_bfloat16* y, int sms, cudaStream_t stream) {
+  constexpr int G = 32 / L;
+  static bool optin = false;  // the ring can exceed the 48 KB default: opt both variants in once
+  if (!optin) {
+    cudaError_t e = cudaFuncSetAttribute(layernorm_kernel<NV, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kLnRingMaxBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(layernorm_kernel<NV, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kLnRingMaxBytes);
+    if (e != cudaSuccess) return e;
+    optin = true;
+  }
+  const size_t smem = static_cast<size_t>(kLnWarps) * kLnStages * (static_cast<size_t>(G) * c * 2 + sizeof(uint64_t));
+  // blocks that fit one SM: the launch bound or the shared-memory ring (228 KB per SM, 1 KB reserved per block)
+  int per_sm = ln_blocks_per_sm(NV);
+  const int by_smem = static_cast<int>((228u * 1024u) / (smem + 1024u));
+  if (by_smem < per_sm) per_sm = by_smem;
+  const long long resident = static_cast<long long>(sms) * per_sm;
+  const long long steps = (rows + G - 1) / G;
+  const long long need = (steps + kLnWarps - 1) / kLnWarps;
+  const unsigned blocks = static_cast<unsigned>(need < resident ? need : resident);
+  auto kern = (add_rowvec != nullptr) ? layernorm_kernel<NV, L, true> : layernorm_kernel<NV, L, false>;
+  CA_KERNEL_LAUNCH(kern, blocks, kLnWarps * 32, smem, stream, x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y);
+  return cudaGetLastError();
+}
+}  // namespace
+
 cudaError_t launch_layernorm(const __nv_bfloat16* x, long long rows, int c, float eps, const float* gamma,
                              const float* beta, const __nv_bfloat16* add_rowvec, long long rows_per_vec,
                              __nv_bfloat16* y_sum, __nv_bfloat16* y, cudaStream_t stream) {
-  if ((c & 7) != 0 || c > 8 * 32 * 8) return cudaErrorInvalidValue;
+  if ((c & 7) != 0 || c < 8 || c > kLnMaxC) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorMisalignedAddress;  // bulk copies of whole rows
+  if (rows <= 0) return cudaSuccess;
+  if (rows >= (1LL << 31) - 64) return cudaErrorInvalidValue;
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
   }
-  const int nv = ((c >> 3) + 31) / 32;
-  const size_t smem = static_cast<size_t>(kLnWarps) * kLnStages * (static_cast<size_t>(c) * 2 + sizeof(uint64_t));
-  // blocks that fit one SM: the launch bound or the shared-memory ring (228 KB per SM, 1 KB reserved per block)
-  int per_sm = ln_blocks_per_sm(nv);
-  const int by_smem = static_cast<int>((228u * 1024u) / (smem + 1024u));
-  if (by_smem < per_sm) per_sm = by_smem;
-  const long long resident = static_cast<long long>(sms) * per_sm;
-  const long long need = (rows + kLnWarps - 1) / kLnWarps;
-  const unsigned blocks = static_cast<unsigned>(need < resident ? need : resident);
   const long long rpv = rows_per_vec > 0 ? rows_per_vec : 1;
-#define CA_LN(NV)                                                                                                      \
-  do {                                                                                                                 \
-    static bool optin = false; /* the ring can exceed the 48 KB default: opt both variants in once */                  \
-    if (!optin) {                                                                                                      \
-      cudaError_t e = cudaFuncSetAttribute(layernorm_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                           kLnRingMaxBytes);                                                           \
-      if (e == cudaSuccess)                                                                                            \
-        e = cudaFuncSetAttribute(layernorm_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                 kLnRingMaxBytes);                                                                     \
-      if (e != cudaSuccess) return e;                                                                                  \
-      optin = true;                                                                                                    \
-    }                                                                                                                  \
-    auto kern = (add_rowvec != nullptr) ? layernorm_kernel<NV, true> : layernorm_kernel<NV, false>;                   \
-    CA_KERNEL_LAUNCH(kern, blocks, kLnWarps * 32, smem, stream, x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum,  \
-                     y);                                                                                               \
-  } while (0)
-  switch (nv) {
-    case 1: CA_LN(1); break;
-    case 2: CA_LN(2); break;
-    case 3: CA_LN(3); break;
-    case 4: CA_LN(4); break;
-    case 5: CA_LN(5); break;
-    case 6: CA_LN(6); break;
-    case 7: CA_LN(7); break;
-    default: CA_LN(8); break;
+  const int nvec = c >> 3;
+  // the narrowest lane group that still keeps gamma / beta in registers
+  int lanes = 32;
+  if ((nvec + 7) / 8 <= kLnHoldMaxNV) lanes = 8;
+  else if ((nvec + 15) / 16 <= kLnHoldMaxNV) lanes = 16;
+  const int nv = (nvec + lanes - 1) / lanes;
+#define CA_LN(NV, L) \
+  return launch_layernorm_t<NV, L>(x, rows, c, eps, gamma, beta, add_rowvec, rpv, y_sum, y, sms, stream)
+  if (lanes == 8) {
+    switch (nv) {
+      case 1: CA_LN(1, 8);
+      case 2: CA_LN(2, 8);
+      case 3: CA_LN(3, 8);
+      case 4: CA_LN(4, 8);
+      default: CA_LN(5, 8);
+    }
+  }
+  if (lanes == 16) {  // nv is 3..5 here: 1 and 2 fit eight lanes
+    switch (nv) {
+      case 3: CA_LN(3, 16);
+      case 4: CA_LN(4, 16);
+      default: CA_LN(5, 16);
+    }
+  }
+  switch (nv) {       // nv is 3..8: at most 2 would fit sixteen lanes
+    case 3: CA_LN(3, 32);
+    case 4: CA_LN(4, 32);
+    case 5: CA_LN(5, 32);
+    case 6: CA_LN(6, 32);
+    case 7: CA_LN(7, 32);
+    default: CA_LN(8, 32);
   }
 #undef CA_LN
-  return cudaGetLastError();
 }
 
 }  // namespace ca

@@ -457,8 +457,19 @@ def run_all(stop_on_fail=False, group=None):
         lambda: check_layernorm(30001, 1280),
         lambda: check_layernorm(70000, 640),
         lambda: check_layernorm(40000, 320, add=True),
-        lambda: check_layernorm(9000, 2048),     # 64 KB ring per block (opt-in shared memory)
+        lambda: check_layernorm(9000, 2048),     # widest row: gamma / beta reloaded per row
         lambda: check_layernorm(5, 8),
+        # lane groups: 8 lanes x 4 rows (C = 320), 16 x 2 (C = 640), short last step, row-vector change inside a step
+        lambda: check_layernorm(40003, 320),
+        lambda: check_layernorm(70001, 640),
+        lambda: check_layernorm(40004, 320, add=True),
+        lambda: check_layernorm(20004, 640, add=True),
+        lambda: check_layernorm(3001, 256),
+        lambda: check_layernorm(3001, 512),
+        lambda: check_layernorm(3001, 768),
+        lambda: check_layernorm(3001, 1024),
+        lambda: check_layernorm(3001, 1288),
+        lambda: check_layernorm(777, 72),
         lambda: check_softmax_rows(300, 4096),
         lambda: check_softmax_rows(64, 16384),
         check_timestep_embedding,
