@@ -84,6 +84,7 @@ SIGNATURES = {
     "ca_router_weights": [_P, _P, _I, _I, _P, _P],
     "ca_router_merge": [_P, _P, _I, _L, _P, _P],
     "ca_softmax_rows": [_P, _L, _L, _P, _P],
+    "ca_frame_conv_small": [_P, _I, _I, _L, _I, _I, _I, _P, _P, _P, _P],
     "ca_cfg_euler": [_P, _P, _P, _L, _F, _P, _I, _P, _P, _P],
     "ca_cfg_euler_v": [_P, _P, _P, _L, _P, _I, _L, _P, _I, _P, _P, _P],
     "ca_cfg_ddim": [_P, _P, _P, _L, _F, _P, _I, _I, _P, _P, _P],

@@ -71,32 +71,40 @@ def shared_timestep(timestep, device) -> torch.Tensor:
 
 class AlphaBlender(Packable):
     """Learned mix factor; alpha = sigmoid(mix_factor) in the parameter dtype (image_only_indicator is all zeros on
-    this path, adapter_spatial_temporal.py:200).  The blend itself is fused into the producing GEMM's epilogue."""
+    this path, adapter_spatial_temporal.py:200).  The blend itself is fused into the producing GEMM's epilogue, which
+    computes alpha * x_spatial + bf16(1 - alpha) * x_temporal.
+    switch_spatial_to_temporal_mix (the temporal VAE decoder's blocks): diffusers replaces alpha by 1 - alpha first, in
+    the activation dtype, so the value handed to the epilogue is bf16(1 - bf16(sigmoid(mix_factor)))."""
 
-    def __init__(self, alpha: float = 0.5):
+    def __init__(self, alpha: float = 0.5, switch_spatial_to_temporal_mix: bool = False):
         super().__init__()
+        self.switch_spatial_to_temporal_mix = switch_spatial_to_temporal_mix
         self.mix_factor = nn.Parameter(torch.tensor([alpha]))
 
     def pack(self):
-        return torch.sigmoid(self.mix_factor.detach().to(BF16)).float().contiguous()
+        a = torch.sigmoid(self.mix_factor.detach().to(BF16))
+        if self.switch_spatial_to_temporal_mix:
+            a = 1.0 - a
+        return a.float().contiguous()
 
     def alpha(self):
         return self.packed()
 
 
 class TemporalResnetBlock(nn.Module):
-    """diffusers TemporalResnetBlock on [B*F, H, W, C]: 5-D GroupNorm statistics over (C/32, F, H, W), Conv3d (3,1,1)."""
+    """diffusers TemporalResnetBlock on [B*F, H, W, C]: 5-D GroupNorm statistics over (C/32, F, H, W), Conv3d (3,1,1).
+    temb_channels None (the temporal VAE decoder): no time-embedding projection."""
 
-    def __init__(self, c: int, temb_channels: int, eps: float):
+    def __init__(self, c: int, temb_channels: Optional[int], eps: float):
         super().__init__()
         self.norm1 = Norm(c, eps)
         self.conv1 = TemporalConv(c, c)
-        self.time_emb_proj = Linear(temb_channels, c)
+        self.time_emb_proj = Linear(temb_channels, c) if temb_channels is not None else None
         self.norm2 = Norm(c, eps)
         self.conv2 = TemporalConv(c, c)
 
     def forward(self, x, frames: int, temb_act, blend_src=None, blend_alpha=None):
-        tp = self.time_emb_proj(temb_act)  # [B*F or 1, C]
+        tp = self.time_emb_proj(temb_act) if self.time_emb_proj is not None else None  # [B*F or 1, C]
         h = self.norm1.group_norm(x, silu=True, imgs_per_sample=frames)
         h = self.conv1(h, frames, rowvec=tp)
         h = self.norm2.group_norm(h, silu=True, imgs_per_sample=frames)

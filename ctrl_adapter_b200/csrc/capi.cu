@@ -344,6 +344,12 @@ int ca_i2vgen_latent_encoder(const void* x, int32_t clips, int32_t frames, int64
   CA_LAUNCH(ca::launch_i2vgen_latent_encoder((const __nv_bfloat16*)x, clips, frames, hw, c_stride, params,
                                              (__nv_bfloat16*)y, (cudaStream_t)s), "i2vgen_latent_encoder");
 }
+int ca_frame_conv_small(const void* x, int32_t clips, int32_t frames, int64_t hw, int32_t c_stride, int32_t cin,
+                        int32_t cout, const float* w_host, const float* bias_host, void* y, void* s) {
+  if (w_host == nullptr) return fail(CA_ERR_INVALID, "frame_conv_small: null weight pointer");
+  CA_LAUNCH(ca::launch_frame_conv_small((const __nv_bfloat16*)x, clips, frames, hw, c_stride, cin, cout, w_host,
+                                        bias_host, (__nv_bfloat16*)y, (cudaStream_t)s), "frame_conv_small");
+}
 int ca_softmax_rows(const float* x, int64_t rows, int64_t cols, void* y, void* s) {
   CA_LAUNCH(ca::launch_softmax_rows(x, rows, cols, (__nv_bfloat16*)y, (cudaStream_t)s), "softmax_rows");
 }

@@ -497,6 +497,73 @@ cudaError_t launch_i2vgen_latent_encoder(const __nv_bfloat16* x, int clips, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Conv3d (3,1,1), padding (1,0,0) over the frame axis for a handful of channels: the SVD temporal decoder's
+// time_conv_out (3 -> 3 on the decoded RGB frames; diffusers TemporalDecoder.forward, reached from the svd pipeline's
+// decode_latents :265-292).  Far too narrow for the tensor-core GEMM (K = 9), and HBM-bound: one thread per pixel pair
+// reads the (up to) three frames' 16-byte channel vectors of conv_out's zero-padded channels-last output and writes the
+// planes of the logical NCHW result directly (the layout conversion is fused).  fp32 accumulation, one rounding to bf16.
+// The 27 + 3 parameters travel in the kernel parameter space.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+frame_conv_small_kernel(const __nv_bfloat16* __restrict__ x, int frames, long long hw, int c_stride, int cin, int cout,
+                        FrameConvSmallParams prm, __nv_bfloat16* __restrict__ y) {
+  CA_PDL_TRIGGER();
+  CA_PDL_WAIT();
+  const long long img = blockIdx.y;           // clip * frames + f
+  const int f = static_cast<int>(img % frames);
+  const long long p0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  if (p0 >= hw) return;
+  const bool two = p0 + 1 < hw;
+  float acc[2][kFrameConvMaxC];
+#pragma unroll
+  for (int co = 0; co < kFrameConvMaxC; ++co) acc[0][co] = acc[1][co] = prm.b[co];
+#pragma unroll
+  for (int dt = 0; dt < 3; ++dt) {
+    const int fs = f + dt - 1;
+    if (fs < 0 || fs >= frames) continue;     // zero padding in time
+    const __nv_bfloat16* src = x + ((img + dt - 1) * hw + p0) * c_stride;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (q == 1 && !two) break;
+      const uint2 u = *reinterpret_cast<const uint2*>(src + static_cast<long long>(q) * c_stride);  // channels 0..3
+      const float xv[4] = {bf16lo_to_float(u.x), bf16hi_to_float(u.x), bf16lo_to_float(u.y), bf16hi_to_float(u.y)};
+#pragma unroll
+      for (int co = 0; co < kFrameConvMaxC; ++co)
+#pragma unroll
+        for (int ci = 0; ci < kFrameConvMaxC; ++ci)
+          if (co < cout && ci < cin) acc[q][co] = fmaf(prm.w[co][ci][dt], xv[ci], acc[q][co]);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < kFrameConvMaxC; ++co) {
+    if (co >= cout) break;
+    __nv_bfloat16* dst = y + (img * cout + co) * hw + p0;
+    if (two && (hw & 1) == 0) {
+      *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[0][co], acc[1][co]);
+    } else {
+      dst[0] = __float2bfloat16_rn(acc[0][co]);
+      if (two) dst[1] = __float2bfloat16_rn(acc[1][co]);
+    }
+  }
+}
+cudaError_t launch_frame_conv_small(const __nv_bfloat16* x, int clips, int frames, long long hw, int c_stride, int cin,
+                                    int cout, const float* w_host, const float* bias_host, __nv_bfloat16* y,
+                                    cudaStream_t stream) {
+  if (clips < 1 || frames < 1 || hw < 1 || cin < 1 || cout < 1 || cin > kFrameConvMaxC || cout > kFrameConvMaxC ||
+      c_stride < 4 || (c_stride & 3) != 0 || static_cast<long long>(clips) * frames > 65535)
+    return cudaErrorInvalidValue;
+  FrameConvSmallParams prm = {};
+  for (int co = 0; co < cout; ++co) {
+    prm.b[co] = bias_host != nullptr ? bias_host[co] : 0.f;
+    for (int ci = 0; ci < cin; ++ci)
+      for (int dt = 0; dt < 3; ++dt) prm.w[co][ci][dt] = w_host[(co * cin + ci) * 3 + dt];
+  }
+  const dim3 grid(static_cast<unsigned>((hw + 511) / 512), static_cast<unsigned>(clips * frames));
+  CA_KERNEL_LAUNCH(frame_conv_small_kernel, grid, 256, 0, stream, x, frames, hw, c_stride, cin, cout, prm, y);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row softmax, fp32 scores -> bf16 probabilities: the VAE decoder's single 512-wide attention head (diffusers
 // AutoencoderKL mid block) is run as  S = Q K^T (tensor-core GEMM, fp32 out)  ->  this kernel  ->  O = P V (GEMM); its
 // head dim is outside attention_kernel's 64 / 128 / 192 and it runs once per generation, not per step.  One CTA per

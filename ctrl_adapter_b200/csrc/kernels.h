@@ -94,6 +94,14 @@ cudaError_t launch_upsample2x(const __nv_bfloat16* x, int n, int h, int w, int c
                               cudaStream_t stream);
 cudaError_t launch_router_weights(const float* logits, const unsigned char* mask, int nrouters, int nexperts,
                                   float* weights, cudaStream_t stream);
+constexpr int kFrameConvMaxC = 4;
+struct FrameConvSmallParams {
+  float w[kFrameConvMaxC][kFrameConvMaxC][3];  // [out channel][in channel][frame tap]
+  float b[kFrameConvMaxC];
+};
+cudaError_t launch_frame_conv_small(const __nv_bfloat16* x, int clips, int frames, long long hw, int c_stride, int cin,
+                                    int cout, const float* w_host, const float* bias_host, __nv_bfloat16* y,
+                                    cudaStream_t stream);
 cudaError_t launch_softmax_rows(const float* x, long long rows, long long cols, __nv_bfloat16* y, cudaStream_t stream);
 static constexpr int kMaxRouterExperts = 8;
 cudaError_t launch_router_merge(const __nv_bfloat16* const* xs_host, const float* w, int nactive, long long n,

@@ -519,6 +519,28 @@ def softmax_rows(x: torch.Tensor):
     return y
 
 
+def frame_conv_small(x: torch.Tensor, w_host: torch.Tensor, bias_host: Optional[torch.Tensor], frames: int, cin: int):
+    """Conv3d (3,1,1), padding (1,0,0) over the frame axis for <= 4 channels (the temporal VAE decoder's time_conv_out).
+    x [B*F, H, W, Cs] channels-last bf16 (the first `cin` channels are read); w_host [Cout, Cin, 3] / bias_host [Cout]:
+    fp32 HOST tensors (passed to the kernel by value).  Returns [B*F, Cout, H, W] bf16 (logical NCHW, contiguous)."""
+    _req(x)
+    if w_host.device.type != "cpu" or w_host.dtype != torch.float32 or not w_host.is_contiguous():
+        raise ValueError("frame_conv_small: weights must be a contiguous fp32 host tensor")
+    bf, h, w_, cs = x.shape
+    cout = w_host.shape[0]
+    if tuple(w_host.shape) != (cout, cin, 3) or bf % frames:
+        raise ValueError("frame_conv_small: weight shape / frame count mismatch")
+    y = torch.empty((bf, cout, h, w_), device=x.device, dtype=BF16)
+    bptr = None
+    if bias_host is not None:
+        if bias_host.device.type != "cpu" or bias_host.dtype != torch.float32 or bias_host.numel() != cout:
+            raise ValueError("frame_conv_small: bias must be an fp32 host tensor of Cout elements")
+        bptr = bias_host.data_ptr()
+    _launch("frame_conv_small", 0.0, 2.0 * (x.numel() + y.numel()), "ca_frame_conv_small", x.data_ptr(), bf // frames, frames,
+            h * w_, cs, cin, cout, w_host.data_ptr(), bptr, y.data_ptr(), _stream())
+    return y
+
+
 def router_weights(logits: torch.Tensor, mask: Optional[torch.Tensor]):
     """logits [R, E] fp32, mask [E] uint8 (0 = masked) -> softmax weights [R, E] fp32."""
     _req(logits, torch.float32)

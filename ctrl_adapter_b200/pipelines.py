@@ -28,7 +28,7 @@ from .controlnet import MultiControlNetModel
 from .pipeline_i2vgen import I2VGenXLControlNetAdapterLoop
 from .pipeline_sdxl import SDXLControlNetAdapterLoop
 from .pipeline_svd import SVDControlNetAdapterLoop
-from .vae import decode_latents, tensor2vid
+from .vae import decode_latents, svd_decode_latents, tensor2vid
 from .vae import postprocess as vae_postprocess
 
 BF16 = torch.bfloat16
@@ -386,6 +386,10 @@ class SVDControlNetAdapterPipeline(DiffusionPipeline):
                               feature_extractor=feature_extractor, controlnet=controlnet, adapter=adapter, helper=helper)
         self.vae_scale_factor = 8
 
+    def decode_latents(self, latents: torch.Tensor, num_frames: int, decode_chunk_size: int = 14):
+        """svd pipeline :265-292: (B, F, 4, h, w) latents -> (B, 3, F, H, W) fp32 frames in [-1, 1]."""
+        return svd_decode_latents(_vae(self), latents, num_frames, decode_chunk_size)
+
     @torch.no_grad()
     def __call__(self, image=None, prompt: str = "", height: int = 576, width: int = 1024,
                  num_frames: Optional[int] = None, num_inference_steps: int = 25, min_guidance_scale: float = 1.0,
@@ -450,12 +454,9 @@ class SVDControlNetAdapterPipeline(DiffusionPipeline):
         if output_type == "latent":
             frames = latents
         else:
-            # SVD decodes with AutoencoderKLTemporalDecoder (svd pipeline :265-292), a different model that this package
-            # does not contain: a user-supplied pipeline-level decode_latents is used when present
-            _vae(self)
-            decode = _need(getattr(self, "decode_latents", None), "a decode_latents method / output_type='latent'",
-                           "temporal VAE decoder")
-            frames = decode(latents, f, decode_chunk_size)
+            # svd pipeline :495, :787-792: AutoencoderKLTemporalDecoder over chunks of decode_chunk_size frames
+            chunk = decode_chunk_size if decode_chunk_size is not None else f
+            frames = tensor2vid(self.decode_latents(latents, f, chunk), output_type)
         if not return_dict:
             return frames
         return StableVideoDiffusionPipelineOutput(frames=frames, down_block_weights=None, mid_block_weights=None)

@@ -168,6 +168,12 @@ int ca_router_weights(const float* logits, const uint8_t* mask, int32_t nrouters
  * head (diffusers AutoencoderKL mid block, reached from sdxl pipeline :1414 / i2vgen pipeline :398-418) runs as
  * GEMM (QK^T, fp32) -> this -> GEMM (PV).  softmax in fp32, one rounding to bf16 (torch SDPA math semantics). */
 int ca_softmax_rows(const float* x, int64_t rows, int64_t cols, void* y, void* cuda_stream);
+/* Conv3d (3,1,1), padding (1,0,0) over the frame axis for <= 4 channels: time_conv_out of the SVD VAE's TemporalDecoder
+ * (diffusers AutoencoderKLTemporalDecoder, run by the svd pipeline's decode_latents :265-292).  x: channels-last bf16
+ * [clips*frames, hw, c_stride] (the first cin channels are read); w / bias: HOST arrays [cout][cin][3] / [cout] (they
+ * travel to the kernel by value, so the call is CUDA-graph capturable); y: bf16 [clips*frames, cout, hw] (logical NCHW). */
+int ca_frame_conv_small(const void* x, int32_t clips, int32_t frames, int64_t hw, int32_t c_stride, int32_t cin,
+                        int32_t cout, const float* w_host, const float* bias_host, void* y, void* cuda_stream);
 /* Weighted merge of expert residuals (i2vgen_xl pipeline :1001-1022): y = sum_e w[e] * xs[e], bf16 rounding
  * after each multiply and each add as in the reference loop.  xs: HOST array of nactive (<= 8) device pointers; they
  * travel to the kernel by value, so the call is CUDA-graph capturable. */

@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .blocks import ResnetBlock2D, Upsample2D
+from .blocks import ResnetBlock2D, SpatioTemporalResBlock, Upsample2D
 
 
 class VaeAttention(nn.Module):
@@ -117,3 +117,93 @@ class AutoencoderKL(nn.Module):
 
     def decode(self, z, return_dict=False):
         return (self.decoder(self.post_quant_conv(z)),)
+
+
+# ---- SVD: diffusers v0.27.2 models/autoencoders/autoencoder_kl_temporal_decoder.py (TemporalDecoder,
+# AutoencoderKLTemporalDecoder.decode) and models/unets/unet_3d_blocks.py (MidBlockTemporalDecoder,
+# UpBlockTemporalDecoder), restated; what ``self.vae.decode(..., num_frames=)`` runs in
+# /root/reference/svd/pipelines/svd_controlnet_adapter_pipeline.py:265-292.  Parity unpinned like the rest of this file.
+def _st_block(cin, cout):
+    return SpatioTemporalResBlock(in_channels=cin, out_channels=cout, temb_channels=None, eps=1e-6, temporal_eps=1e-5,
+                                  merge_factor=0.0, merge_strategy="learned", switch_spatial_to_temporal_mix=True)
+
+
+class MidBlockTemporalDecoder(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, attention_head_dim: int = 512, num_layers: int = 1):
+        super().__init__()
+        self.resnets = nn.ModuleList([_st_block(in_channels if i == 0 else out_channels, out_channels)
+                                      for i in range(num_layers)])
+        self.attentions = nn.ModuleList([VaeAttention(in_channels, attention_head_dim, 32, 1e-6)])
+
+    def forward(self, hidden_states, image_only_indicator):
+        hidden_states = self.resnets[0](hidden_states, image_only_indicator=image_only_indicator)
+        for resnet, attn in zip(self.resnets[1:], self.attentions):
+            hidden_states = attn(hidden_states)
+            hidden_states = resnet(hidden_states, image_only_indicator=image_only_indicator)
+        return hidden_states
+
+
+class UpBlockTemporalDecoder(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, num_layers: int = 1, add_upsample: bool = True):
+        super().__init__()
+        self.resnets = nn.ModuleList([_st_block(in_channels if i == 0 else out_channels, out_channels)
+                                      for i in range(num_layers)])
+        self.upsamplers = nn.ModuleList([Upsample2D(out_channels, use_conv=True, out_channels=out_channels)]) \
+            if add_upsample else None
+
+    def forward(self, hidden_states, image_only_indicator):
+        for resnet in self.resnets:
+            hidden_states = resnet(hidden_states, image_only_indicator=image_only_indicator)
+        if self.upsamplers is not None:
+            for up in self.upsamplers:
+                hidden_states = up(hidden_states)
+        return hidden_states
+
+
+class TemporalDecoder(nn.Module):
+    def __init__(self, in_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2):
+        super().__init__()
+        self.conv_in = nn.Conv2d(in_channels, block_out_channels[-1], kernel_size=3, stride=1, padding=1)
+        self.mid_block = MidBlockTemporalDecoder(num_layers=layers_per_block, in_channels=block_out_channels[-1],
+                                                 out_channels=block_out_channels[-1],
+                                                 attention_head_dim=block_out_channels[-1])
+        self.up_blocks = nn.ModuleList([])
+        rev = list(reversed(block_out_channels))
+        out_c = rev[0]
+        for i, c in enumerate(rev):
+            prev, out_c = out_c, c
+            self.up_blocks.append(UpBlockTemporalDecoder(num_layers=layers_per_block + 1, in_channels=prev,
+                                                         out_channels=out_c, add_upsample=i != len(rev) - 1))
+        self.conv_norm_out = nn.GroupNorm(num_channels=block_out_channels[0], num_groups=32, eps=1e-6)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(block_out_channels[0], out_channels, 3, padding=1)
+        self.time_conv_out = nn.Conv3d(out_channels, out_channels, kernel_size=(3, 1, 1), padding=(1, 0, 0))
+
+    def forward(self, sample, image_only_indicator, num_frames: int = 1):
+        sample = self.conv_in(sample)
+        upscale_dtype = next(iter(self.up_blocks.parameters())).dtype
+        sample = self.mid_block(sample, image_only_indicator=image_only_indicator)
+        sample = sample.to(upscale_dtype)
+        for up_block in self.up_blocks:
+            sample = up_block(sample, image_only_indicator=image_only_indicator)
+        sample = self.conv_out(self.conv_act(self.conv_norm_out(sample)))
+        batch_frames, channels, height, width = sample.shape
+        batch_size = batch_frames // num_frames
+        sample = sample[None, :].reshape(batch_size, num_frames, channels, height, width).permute(0, 2, 1, 3, 4)
+        sample = self.time_conv_out(sample)
+        return sample.permute(0, 2, 1, 3, 4).reshape(batch_frames, channels, height, width)
+
+
+class AutoencoderKLTemporalDecoder(nn.Module):
+    """decode() half only (no post_quant_conv in this model): image_only_indicator = zeros(batch, num_frames)."""
+
+    def __init__(self, in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 latent_channels=4, scaling_factor=0.18215, **_unused):
+        super().__init__()
+        self.scaling_factor = scaling_factor
+        self.decoder = TemporalDecoder(latent_channels, out_channels, block_out_channels, layers_per_block)
+
+    def decode(self, z, num_frames: int = 1, return_dict=False):
+        batch_size = z.shape[0] // num_frames
+        image_only_indicator = torch.zeros(batch_size, num_frames, dtype=z.dtype, device=z.device)
+        return (self.decoder(z, num_frames=num_frames, image_only_indicator=image_only_indicator),)

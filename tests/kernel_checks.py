@@ -299,6 +299,19 @@ def check_layernorm(rows, c, *, add=False, seed=0):
     return _report(f"layernorm rows{rows} c{c} add={int(add)}", out, ref, 2 ** -7, 2e-3)
 
 
+def check_frame_conv_small(clips, frames, h, w, cin=3, cout=3, seed=0):
+    ops = _ops()
+    x = _rand(clips * frames, h, w, 8, seed=seed + 1)
+    wt = (_rand(cout, cin, 3, seed=seed + 2, dtype=torch.float32) * 0.5).to(BF16).float().cpu().contiguous()
+    b = (_rand(cout, seed=seed + 3, dtype=torch.float32) * 0.3).to(BF16).float().cpu().contiguous()
+    y = ops.frame_conv_small(x, wt, b, frames, cin)
+    xs = x[..., :cin].float().reshape(clips, frames, h, w, cin).permute(0, 4, 1, 2, 3)
+    ref = F.conv3d(xs, wt.cuda()[:, :, :, None, None], b.cuda(), padding=(1, 0, 0))
+    ref = ref.permute(0, 2, 1, 3, 4).reshape(clips * frames, cout, h, w).to(BF16).float()
+    torch.cuda.synchronize()
+    return _report(f"frame_conv_small {clips}x{frames} frames {h}x{w} {cin}->{cout}", y, ref, 2 ** -7, 2e-3)
+
+
 def check_timestep_embedding(seed=0):
     ops = _ops()
     t = torch.tensor([999.0, 981.0, 501.0, 1.0, 0.0, 13.0], device="cuda")
@@ -470,6 +483,9 @@ def run_all(stop_on_fail=False, group=None):
         lambda: check_layernorm(3001, 1024),
         lambda: check_layernorm(3001, 1288),
         lambda: check_layernorm(777, 72),
+        lambda: check_frame_conv_small(2, 5, 16, 24),
+        lambda: check_frame_conv_small(1, 1, 5, 7),          # one frame (both neighbours padded), odd pixel count
+        lambda: check_frame_conv_small(3, 2, 9, 5, cin=4, cout=2),
         lambda: check_softmax_rows(300, 4096),
         lambda: check_softmax_rows(64, 16384),
         check_timestep_embedding,

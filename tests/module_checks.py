@@ -229,6 +229,25 @@ def check_vae(n=2, r=32):
     return _compare(f"AutoencoderKL.decode n={n} latents {r}x{r}", ours, ref, eager, tol_rel=3e-2, tol_max=8e-2)
 
 
+def check_vae_temporal(clips=1, frames=4, h=32, w=32):
+    """AutoencoderKLTemporalDecoder.decode (the SVD VAE) at the published width vs the restated diffusers decoder: fp32
+    truth and its eager bf16-autocast run.  clips * frames latents, `frames` per temporal unit."""
+    from ctrl_adapter_b200.vae import AutoencoderKLTemporalDecoder
+    from oracle.vae import AutoencoderKLTemporalDecoder as OV
+    from oracle.weights import seeded_tensor
+    inputs = dict(z=seeded_tensor("vae_t_z", (clips * frames, 4, h, w)))
+    call = lambda m, i: m.decode(i["z"], num_frames=frames)[0]  # noqa: E731
+    sd, ref, eager, inp16 = _oracle_runs(lambda: OV(), 12, inputs, call)
+    with torch.device("cuda"):
+        ours_m = AutoencoderKLTemporalDecoder()
+    ours_m.load_state_dict(sd)
+    ours_m = ours_m.to(BF16).cuda().eval()
+    ours = ours_m.decode(inp16["z"], num_frames=frames).sample
+    torch.cuda.synchronize()
+    return _compare(f"AutoencoderKLTemporalDecoder.decode {clips}x{frames} frames, latents {h}x{w}", ours, ref, eager,
+                    tol_rel=3e-2, tol_max=8e-2)
+
+
 def _build_pair(make_oracle, make_ours, seed):
     """oracle (fp32, bf16-quantised weights, on GPU) and our module with identical weights."""
     from oracle.weights import seeded_init_
@@ -462,7 +481,8 @@ GROUPS = {
     "controlnet": [lambda: check_controlnet(2, 8), lambda: check_controlnet(2, 16, True, 0.75)],
     "unet": [lambda: check_unet_sdxl(2, 16, True), lambda: check_unet_sdxl(1, 32, False)],
     "video": [lambda: check_unet_i2vgen(1, 4, 32, True), lambda: check_unet_i2vgen(2, 2, 32, False)],
-    "vae": [lambda: check_vae(2, 32), lambda: check_vae(1, 64)],
+    "vae": [lambda: check_vae(2, 32), lambda: check_vae(1, 64), lambda: check_vae_temporal(1, 4, 32, 32),
+            lambda: check_vae_temporal(2, 3, 16, 24)],
     "svd": [lambda: check_unet_svd(2, 4, 32, True), lambda: check_unet_svd(1, 3, 16, False)],
     "sparse": [lambda: check_step_i2vgen(2, False, sparse=[0, 2])],
     "fold": [check_controlnet_folded],

@@ -249,6 +249,15 @@ def softmax_rows(x):
     return torch.softmax(x.float(), dim=-1).to(BF16)
 
 
+def frame_conv_small(x, w_host, bias_host, frames, cin):
+    bf, h, w_, cs = x.shape
+    b = bf // frames
+    xs = x[..., :cin].float().reshape(b, frames, h, w_, cin).permute(0, 4, 1, 2, 3)   # [B, Cin, F, H, W]
+    wt = w_host.float().to(x.device)[:, :, :, None, None]
+    y = F.conv3d(xs, wt, None if bias_host is None else bias_host.float().to(x.device), padding=(1, 0, 0))
+    return y.permute(0, 2, 1, 3, 4).reshape(bf, -1, h, w_).to(BF16).contiguous()
+
+
 def router_weights(logits, mask):
     lg = logits.float().clone()
     if mask is not None:
@@ -328,7 +337,7 @@ def cfg_ddim(eps_uncond, eps_text, latents, guidance, step_row, latents_out=None
 
 _EMULATED = ["linear", "conv2d", "temporal_conv", "attention", "temporal_attention", "group_norm", "layer_norm",
              "timestep_embedding", "silu", "add", "nchw_to_nhwc", "nhwc_to_nchw", "avgpool", "upsample2x", "i2vgen_latent_encoder",
-             "softmax_rows", "router_weights", "router_merge", "cfg_euler", "cfg_euler_v", "cfg_ddim"]
+             "softmax_rows", "frame_conv_small", "router_weights", "router_merge", "cfg_euler", "cfg_euler_v", "cfg_ddim"]
 
 
 @contextlib.contextmanager

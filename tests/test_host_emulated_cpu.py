@@ -148,6 +148,49 @@ def test_emulated_vae_decoder():
     assert tensor2vid(vid, "pt").shape == (1, 2, 3, 64, 64)
 
 
+def test_emulated_vae_temporal_decoder():
+    """AutoencoderKLTemporalDecoder.decode (the SVD VAE, svd pipeline :265-292) through the emulated op layer vs the
+    restated diffusers decoder: SpatioTemporalResBlocks with the switched learned alpha (mix factors moved off 0 so the
+    switch matters), temporal eps 1e-5 vs spatial 1e-6, time_conv_out over the frames of the chunk, chunked
+    decode_latents (a chunk is one temporal unit, also across clips)."""
+    from ctrl_adapter_b200.vae import AutoencoderKLTemporalDecoder, svd_decode_latents
+    from oracle.vae import AutoencoderKLTemporalDecoder as OV
+    from oracle.weights import seeded_tensor
+    kw = dict(block_out_channels=(32, 64, 64), layers_per_block=1)
+    o = seeded_init_(OV(**kw), 12).eval()
+    with torch.no_grad():
+        for i, (n_, p_) in enumerate(o.named_parameters()):
+            if n_.endswith("mix_factor"):
+                p_.fill_(0.8 - 0.35 * i % 1.7)
+    m = AutoencoderKLTemporalDecoder(**kw)
+    sd = dict(o.state_dict())
+    sd["encoder.conv_in.weight"] = torch.zeros(1)
+    sd["quant_conv.weight"] = torch.zeros(1)
+    m.load_state_dict(sd)
+    for p_ in o.parameters():
+        p_.data = _q(p_.data)
+    m = m.to(BF16).eval()
+    z = _q(seeded_tensor("vae_t_z", (6, 4, 8, 8)))
+    with torch.no_grad(), emu.patched_ops():
+        ref = o.decode(z, num_frames=3)[0]
+        out = m.decode(z, num_frames=3).sample
+        # two clips of 3 frames decoded 4 frames at a time: chunks [0:4] and [4:6] are the temporal units
+        vid = svd_decode_latents(m, z.reshape(2, 3, 4, 8, 8) * m.config.scaling_factor, 3, decode_chunk_size=4)
+        ref_chunks = torch.cat([o.decode(z[:4], num_frames=4)[0], o.decode(z[4:], num_frames=2)[0]])
+    assert out.shape == ref.shape == (6, 3, 32, 32)
+    rel = float((out.float() - ref).norm() / ref.norm())
+    assert rel <= 3e-2, rel
+    # the temporal path is live: decoding the same frames as single-frame units gives a different answer
+    with torch.no_grad(), emu.patched_ops():
+        single = m.decode(z, num_frames=1).sample
+    assert float((single.float() - out.float()).abs().max()) > 1e-2
+    assert vid.shape == (2, 3, 3, 32, 32) and vid.dtype == torch.float32
+    v = vid.permute(0, 2, 1, 3, 4).reshape(6, 3, 32, 32)
+    assert float((v - ref_chunks).norm() / ref_chunks.norm()) <= 3e-2
+    with pytest.raises(ValueError):
+        m.decode(z[:5], num_frames=3)
+
+
 @pytest.mark.slow
 def test_emulated_unet_svd():
     """Two clips with DIFFERENT image tokens + 5-D residuals with surplus entries: covers the per-clip broadcast rows and
