@@ -9,10 +9,9 @@ kernel, both AlphaBlender mixes are fused into the producing GEMM epilogue, and 
 second TMA source.  The conditioning of this backbone is ONE CLIP image token per clip, so every cross-attention
 collapses exactly to a per-clip broadcast vector to_out(to_v(ctx)) (same identity as the adapter's quirk Q5).
 
-STATUS: composed from building blocks that are GPU-validated through the adapter and I2VGen-XL paths; the composition
-itself is verified on CPU (tests/test_host_emulated_cpu.py: this module over an emulation of the op layer vs the restated
-reference class, which in turn is bit-exact against the reference's own class), but its GPU parity check
-(tests/test_zz_svd_gpu.py) has had no hardware run yet and reports xfail instead of red until it has.
+Parity: GPU groups `svd`, `svd_loop` (tests/test_video_paths_gpu.py) against the restated reference class, which is
+bit-exact against the reference's own class; the composition is also checked on CPU over an emulation of the op layer
+(tests/test_host_emulated_cpu.py).
 """
 from __future__ import annotations
 
