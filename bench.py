@@ -18,8 +18,9 @@ One "step" = one iteration of the pipeline loop for the whole per-GPU batch:
 Step-invariant work (prompt K/V projections, the ControlNet's conditioning-image embedding, router weights) is done once
 in prepare(), outside the timed steps, exactly as a pipeline call would do it once per generation.
 
-Every line carries, next to `value` (CUDA-graph replay, inputs resident in HBM): `e2e` (eager module forward()s through
-the C ABI with pinned host latents copied in/out every step), `roofline` (dominant kernel family, CUDA events),
+Every line carries, next to `value` (CUDA-graph replay, inputs resident in HBM): `e2e` (the step as the pipeline classes run it
+-- CUDA-graph replay by default, `--no-graph`: eager module forward()s through the C ABI -- with pinned host latents copied
+in and out every step and the host waiting for each result), `roofline` (dominant kernel family, CUDA events),
 `eager_gpu_baseline` + `vs_eager` (the oracle restatement of the reference loop as eager bf16-autocast PyTorch on the same
 GPU: BASELINE.md's "reference single-GPU eager PyTorch" denominator) and `cpu_baseline` (the same oracle on the host cores).
 
@@ -571,7 +572,7 @@ def main():
         host_in.copy_(loop.model_in.cpu())
         ke = max(3, min(a.steps, 10))
         for _ in range(2):
-            loop.step(0)
+            stepfn(0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -579,7 +580,7 @@ def main():
         for i in range(ke):
             loop.latents.copy_(host_lat, non_blocking=True)       # H2D: this step's latents
             loop.model_in.copy_(host_in, non_blocking=True)       # H2D: scaled model input
-            loop.step(i % nsteps)                                 # ControlNet / adapter / UNet module forward()s
+            stepfn(i % nsteps)                                    # the pipeline classes' step (graph replay unless --no-graph)
             host_lat.copy_(loop.latents, non_blocking=True)       # D2H: the step's result
             host_in.copy_(loop.model_in, non_blocking=True)
             torch.cuda.current_stream().synchronize()             # the host consumes the result every step
@@ -594,7 +595,9 @@ def main():
         nbytes = host_lat.numel() * 4 + host_in.numel() * 2
         e2e = {"value": world * ke / (ms_e / 1000.0), "unit": "steps/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "steps": ke, "ms_per_step": ms_e / ke, "wall_ms_per_step": 1000 * wall / ke,
-               "path": "eager module forward() calls through the C ABI, pinned host latents copied in/out every step"}
+               "path": ("CUDA-graph replay of the step (the pipeline classes' default)" if use_graph else
+                        "eager module forward() calls through the C ABI") +
+                       ", pinned host latents copied in/out every step, host waits for every result"}
 
     # ---- per-kernel-family CUDA-event profile of one eager step -> roofline of the dominant kernel ----
     roofline, families = None, None
