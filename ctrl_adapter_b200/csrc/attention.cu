@@ -560,6 +560,284 @@ attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Short-KV variant: Lk <= 80 (the 77-token text cross attention of the ControlNet / SDXL UNet), head dim 64.
+// There is ONE KV tile per work item, so the tile loop that hides the PV latency and the output write in the general
+// kernel does not exist: there the four softmax warps wait for PV(i), then write item i out, and only then start on
+// item i + 1 (profiles/r2_ncu_attn77.md: 156 TFLOP/s, nothing busy).  Here
+//   * S is M128 x N80 and P 40 packed cells, which leaves tensor memory for TWO output accumulators
+//     (columns: O0 [0,64)  O1 [64,128)  S [128,208)  P [208,248)),
+//   * the MMA warp issues QK^T(i+1) BEFORE PV(i) (S is free as soon as the softmax has it in registers), and
+//   * the softmax warps write item i - 1 out AFTER they have staged P(i): PV(i) and QK^T(i+1) run under that epilogue.
+// No running max / rescale: one tile is the whole row.  Same producer, barriers and Q / K / V rings as above.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int kShortKV = 80;
+
+template <int POLY>
+__global__ void __launch_bounds__(256, 2)
+attention_short_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<1>;
+  CA_PDL_TRIGGER();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  if (pad + Cfg::kDataBytes + 192 > Cfg::kSmemBytes) __trap();
+  uint8_t* smem_q = smem;
+  uint8_t* smem_kv = smem + Cfg::kQStages * Cfg::kQBytes + Cfg::kPBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* q_full = bars + 14;   // [2]
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 10;   // [2]
+  uint64_t* v_empty = bars + 12;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint64_t* q_empty = bars + 16;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int dpad = 64 * p.v_slices;
+  const int nqt = (p.lq + kTileQ - 1) / kTileQ;
+  const int total_items = nqt * p.batch * p.heads * p.v_slices;
+  auto decode = [&](int w, int& q0, int& b, int& h, int& vs) {
+    q0 = (w % nqt) * kTileQ;
+    const int bh = (w / nqt) % (p.batch * p.heads);
+    vs = w / (nqt * p.batch * p.heads);
+    b = bh / p.heads;
+    h = bh % p.heads;
+  };
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base;         // two accumulators of 64 columns
+  const uint32_t tmem_s = tmem_base + 128;   // 80 fp32 score columns
+  const uint32_t tmem_p = tmem_base + 208;   // 40 cells of packed bf16 P
+  CA_PDL_WAIT();
+
+  if (warp < 4) setmaxnreg_dec<48>();
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++it) {
+        int q0, b, h, vs;
+        decode(w, q0, b, h, vs);
+        const int kvb = b / p.kv_batch_div;
+        const int st = it & 1;
+        const uint32_t free_parity = ((it >> 1) & 1) ^ 1;
+        uint8_t* kv = smem_kv + st * Cfg::kStageBytes;
+        mbar_wait_backoff(&q_empty[st], free_parity, p.backoff_ns);
+        mbar_arrive_expect_tx(&q_full[st], Cfg::kQBytes);
+        tma_load_3d(smem_q + st * Cfg::kQBytes, &tmap_q, &q_full[st], h * dpad, q0, b);
+        mbar_wait_backoff(&k_empty[st], free_parity, p.backoff_ns);
+        mbar_arrive_expect_tx(&k_full[st], kChunkBytes);
+        tma_load_3d(kv, &tmap_k, &k_full[st], h * dpad, 0, kvb);
+        mbar_wait_backoff(&v_empty[st], free_parity, p.backoff_ns);
+        mbar_arrive_expect_tx(&v_full[st], kChunkBytes);
+        tma_load_3d(kv + kChunkBytes, &tmap_v, &v_full[st], h * dpad + vs * 64, 0, kvb);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kShortKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V tile) is MN-major
+      const uint32_t q_base = smem_u32(smem_q);
+      const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                           static_cast<int>(gridDim.x);
+      auto issue_qk = [&](uint32_t i) {
+        const int st = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait_backoff(&q_full[st], ph, p.backoff_ns);
+        mbar_wait(&k_full[st], ph);
+        mbar_wait(s_empty, (i & 1) ^ 1);  // the softmax holds S of the previous item in registers
+        tc_fence_after();
+        const uint32_t q_addr = q_base + st * Cfg::kQBytes;
+        const uint32_t k_addr = smem_u32(smem_kv + st * Cfg::kStageBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = umma_smem_desc_sw128(q_addr + k * 32, 16, 1024);
+          const uint64_t db = umma_smem_desc_sw128(k_addr + k * 32, 16, 1024);
+          umma_bf16_ss(tmem_s, da, db, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+        umma_commit(&q_empty[st]);
+      };
+      if (my_items > 0) issue_qk(0);
+      for (int i = 0; i < my_items; ++i) {
+        if (i + 1 < my_items) issue_qk(i + 1);
+        const int st = i & 1;
+        mbar_wait(&v_full[st], (i >> 1) & 1);
+        mbar_wait_backoff(p_full, i & 1, p.backoff_ns);  // P(i) staged; O[i & 1] was written out two items ago
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(smem_kv + st * Cfg::kStageBytes + kChunkBytes);
+#pragma unroll
+        for (int k = 0; k < kShortKV / 16; ++k) {
+          const uint64_t db = umma_smem_desc_sw128(v_addr + k * 2048, 8192, 1024);
+          umma_bf16_ts(tmem_o + (i & 1) * 64, tmem_p + k * 8, db, idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        umma_commit(&v_empty[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    setmaxnreg_inc<208>();
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(q * 32) << 16;
+    const float sl2 = p.scale_log2;
+    const int lk = p.lk;
+    // writes work item w out: O[buf] / l (PV of that item has completed: the caller waited for o_full)
+    auto write_out = [&](int w, float l, uint32_t buf) {
+      int q0, b, h, vs;
+      decode(w, q0, b, h, vs);
+      const float inv_l = 1.0f / l;
+      const int row = q0 + r;
+      __nv_bfloat16* orow = p.out + static_cast<long long>(b) * p.out_batch_stride +
+                            static_cast<long long>(row) * p.out_row_stride + h * dpad + vs * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tmem_o + lane_sel + buf * 64 + c * 32, ov);
+        tmem_ld_wait();
+        if (row < p.lq) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(ov[u * 8 + e]) * inv_l;
+            *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = make_uint4(
+                pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
+        }
+      }
+      tc_fence_before();  // the O reads are ordered before the next p_full arrive (after which PV may overwrite O[buf])
+    };
+    int w_prev = -1;
+    float l_prev = 1.f;
+    uint32_t i = 0;
+    for (int w = blockIdx.x; w < total_items; w += gridDim.x, ++i) {
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      uint32_t sv[kShortKV];
+      tmem_ld_32x32(tmem_s + lane_sel, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+      tmem_ld_32x32(tmem_s + lane_sel + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+      tmem_ld_32x16(tmem_s + lane_sel + 64, *reinterpret_cast<uint32_t(*)[16]>(&sv[64]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);  // S is in registers: QK^T of the next item may overwrite it
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kShortKV; c += 2) {
+        mx0 = fmaxf(mx0, c < lk ? __uint_as_float(sv[c]) : -INFINITY);
+        mx1 = fmaxf(mx1, c + 1 < lk ? __uint_as_float(sv[c + 1]) : -INFINITY);
+      }
+      const float mneg = -fmaxf(mx0, mx1) * sl2;
+      const uint64_t sl2_2 = pack_f32x2(sl2, sl2), mneg_2 = pack_f32x2(mneg, mneg);
+      uint64_t rs[2] = {pack_f32x2(0.f, 0.f), pack_f32x2(0.f, 0.f)};
+#pragma unroll
+      for (int c = 0; c < kShortKV; c += 2) {
+        const float s0 = c < lk ? __uint_as_float(sv[c]) : -INFINITY;  // keys that do not exist: p = 0
+        const float s1 = c + 1 < lk ? __uint_as_float(sv[c + 1]) : -INFINITY;
+        const uint64_t x = fma_f32x2(pack_f32x2(s0, s1), sl2_2, mneg_2);
+        float x0, x1, p0, p1;
+        unpack_f32x2(x, x0, x1);
+        if (pair_uses_poly<POLY>(c >> 1)) {
+          exp2_poly_x2(x0, x1, p0, p1);
+        } else {
+          p0 = fast_exp2(x0);
+          p1 = fast_exp2(x1);
+        }
+        rs[(c >> 1) & 1] = add_f32x2(rs[(c >> 1) & 1], pack_f32x2(p0, p1));
+        sv[c >> 1] = pack_bf16x2(p0, p1);  // in place: cell c / 2 was consumed at least one iteration ago
+      }
+      float r0, r1;
+      unpack_f32x2(add_f32x2(rs[0], rs[1]), r0, r1);
+      const float l = r0 + r1;
+      if (i > 0) {  // PV(i-1) has read P(i-1) and completed O[(i-1) & 1]
+        mbar_wait(o_full, (i - 1) & 1);
+        tc_fence_after();
+      }
+      tmem_st_32x16(tmem_p + lane_sel, *reinterpret_cast<const uint32_t(*)[16]>(&sv[0]));
+      tmem_st_32x16(tmem_p + lane_sel + 16, *reinterpret_cast<const uint32_t(*)[16]>(&sv[16]));
+      tmem_st_32x8(tmem_p + lane_sel + 32, *reinterpret_cast<const uint32_t(*)[8]>(&sv[32]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (i > 0) write_out(w_prev, l_prev, (i - 1) & 1);  // under PV(i) and QK^T(i+1)
+      w_prev = w;
+      l_prev = l;
+    }
+    if (w_prev >= 0) {
+      mbar_wait(o_full, (i - 1) & 1);
+      tc_fence_after();
+      write_out(w_prev, l_prev, (i - 1) & 1);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int POLY>
+static cudaError_t launch_short(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
+                                cudaStream_t stream) {
+  using Cfg = AttnCfg<1>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_short_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(Cfg::kSmemBytes));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attention_short_kernel<POLY>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  static int resident = 0;
+  if (resident == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || sms < 1) return e != cudaSuccess ? e : cudaErrorInvalidConfiguration;
+    resident = sms * 2;
+  }
+  const long long items = static_cast<long long>((p.lq + kTileQ - 1) / kTileQ) * p.batch * p.heads * p.v_slices;
+  if (items <= 0 || items > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const int grid = static_cast<int>(items < resident ? items : resident);
+  auto kern = attention_short_kernel<POLY>;
+  CA_KERNEL_LAUNCH(kern, grid, 256, Cfg::kSmemBytes, stream, q, k, v, p);
+  return cudaGetLastError();
+}
+
 template <int DQ, int POLY, int NS, int TH = 0>
 static cudaError_t launch_dq(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p,
                              cudaStream_t stream) {
@@ -600,6 +878,9 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
   static const int poly = getenv("CA_ATTN_POLY") ? atoi(getenv("CA_ATTN_POLY")) : kPolyDefault;
   // CA_ATTN_THROTTLE = column pairs per dependency group of the exp schedule throttle (0 = off; 4 or 8)
   static const int th = getenv("CA_ATTN_THROTTLE") ? atoi(getenv("CA_ATTN_THROTTLE")) : kThrottleDefault;
+  // CA_ATTN_SHORT=0: developer A/B switch, sends Lk <= 80 through the general kernel as before
+  static const bool short_kv = !(getenv("CA_ATTN_SHORT") && getenv("CA_ATTN_SHORT")[0] == '0');
+  if (short_kv && p.dqk_chunks == 1 && p.lk >= 1 && p.lk <= kShortKV) return launch_short<kPolyDefault>(q, k, v, p, stream);
   switch (p.dqk_chunks) {
     case 1:
       if (split == 1) {

@@ -457,6 +457,12 @@ def run_all(stop_on_fail=False, group=None):
         lambda: check_attention(2, 5, 1024, 1024, 64, ramp=40.0),
         lambda: check_attention(1, 8, 300, 640, 160, ramp=20.0),
         lambda: check_attention(1, 4, 512, 2048, 64, ramp=4.0),
+        # short-KV kernel (Lk <= 80, head dim <= 64): several work items per persistent CTA (ring / phase wrap-around,
+        # deferred output write of the previous item), Lk = 80 / 33 / 1, partial last query tile, padded head dim
+        lambda: check_attention(16, 20, 1024, 77, 64),
+        lambda: check_attention(8, 16, 700, 80, 64),
+        lambda: check_attention(6, 10, 1280, 33, 40),
+        lambda: check_attention(4, 8, 640, 1, 64),
         lambda: check_temporal_attention(2, 16, 64, 5),
         lambda: check_temporal_attention(1, 14, 100, 10),
         lambda: check_groupnorm(2, 32, 32, 320),
@@ -493,7 +499,7 @@ def run_all(stop_on_fail=False, group=None):
         check_router,
         check_cfg,
     ]
-    groups = {"gemm": (0, 18), "conv": (18, 32), "attn": (32, 45), "misc": (45, len(plan))}
+    groups = {"gemm": (0, 18), "conv": (18, 32), "attn": (32, 49), "misc": (49, len(plan))}
     if group:
         lo, hi = groups[group]
         plan = plan[lo:hi]
