@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "ctrl_adapter_b200", "libctrl_adapter_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KEY = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTCBAR", "LDTM", "STTM", "SYNCS", "MUFU", "FFMA2", "HMMA", "LDGSTS", "BAR"]
+KEY = ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UBLKCP", "UTCBAR", "LDTM", "STTM", "SYNCS", "MUFU", "FFMA2", "HMMA", "LDGSTS", "BAR"]
 kern, hist = None, collections.OrderedDict()
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -26,7 +26,7 @@ for line in sass.splitlines():
         if op.startswith("UTCHMMA") and ".2CTA" in op:
             hist[kern]["UTCHMMA.2CTA"] += 1
 print("# SASS opcode histogram per kernel (cuobjdump -sass of the in-tree libctrl_adapter_b200.so, sm_100a)\n")
-print("Counts of the Blackwell-specific opcodes (tcgen05.mma = UTCHMMA, TMA = UTMALDG, tcgen05.ld/st = LDTM/STTM, "
+print("Counts of the Blackwell-specific opcodes (tcgen05.mma = UTCHMMA, TMA = UTMALDG, cp.async.bulk 1-D = UBLKCP, tcgen05.ld/st = LDTM/STTM, "
       "tcgen05.commit = UTCBAR, mbarrier = SYNCS) and of the legacy tensor path (HMMA) per compiled kernel; `instrs` = all.\n")
 print("| kernel | instrs | " + " | ".join(KEY) + " |")
 print("|---|---|" + "---|" * len(KEY))
