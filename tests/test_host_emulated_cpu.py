@@ -189,6 +189,15 @@ def test_emulated_vae_temporal_decoder():
     assert float((v - ref_chunks).norm() / ref_chunks.norm()) <= 3e-2
     with pytest.raises(ValueError):
         m.decode(z[:5], num_frames=3)
+    # the pipeline class decodes through the same function and post-processes like the reference (:787-792)
+    from ctrl_adapter_b200.pipelines import SVDControlNetAdapterPipeline
+    from ctrl_adapter_b200.vae import tensor2vid
+    pipe = SVDControlNetAdapterPipeline(vae=m, image_encoder=None, unet=None, scheduler=None, feature_extractor=None,
+                                        adapter=None, helper=None, controlnet=None)
+    with torch.no_grad(), emu.patched_ops():
+        v2 = pipe.decode_latents(z.reshape(2, 3, 4, 8, 8) * m.config.scaling_factor, 3, 4)
+    assert float((v2 - vid).abs().max()) == 0.0
+    assert tensor2vid(v2, "np").shape == (2, 3, 32, 32, 3) and len(tensor2vid(v2, "pil")[0]) == 3
 
 
 @pytest.mark.slow
