@@ -7,14 +7,11 @@
 //                a K slot is free as soon as its QK^T retired, so K runs two tiles ahead of the softmax),
 //                warp 1 = MMA issuer + TMEM allocator.  S = Q K^T (M128 N128, K = 64*DQ) into TMEM cols [0,128);
 //                O += P V (M128 N64 K128, V consumed MN-major) ACCUMULATED in TMEM cols [128,192).  Warps 2-3 idle.
-//   warpgroups 1..NS: softmax.  NS = 1: one thread per query row; NS = 2 (default for head dim 64, round 2): TWO
-//                threads per row -- warp w and warp w + 4 own the same 32 TMEM lanes and split the 128 key columns
-//                of the tile 64 / 64.  The row max is combined through a 1 KB shared-memory exchange and a 64-thread
-//                named barrier per warp pair; the row sum and the output columns stay split until the item's epilogue.
-//                Why: ncu (profiles/r2_ncu_attn4k_base.md) showed each softmax warp issuing only 24 % of the cycles,
-//                31 % lost to fixed-latency dependency stalls plus a tail of ~50 back-to-back MUFU.EX2 -- with two
-//                softmax warps per SM sub-partition nothing covers them.  Splitting rows doubles the warps per
-//                sub-partition (4) at half the registers each, same instruction count.
+//   warpgroups 1..NS: softmax.  NS = 1 (the default): one thread per query row.  NS = 2 (CA_ATTN_SPLIT=2, evaluated in
+//                round 2 and NOT adopted -- same time, profiles/r2_ncu_attn4k_split2.md): two threads per row -- warp w
+//                and warp w + 4 own the same 32 TMEM lanes and split the 128 key columns of the tile 64 / 64; the row
+//                max is combined through a 1 KB shared-memory exchange and a 64-thread named barrier per warp pair,
+//                the row sum and the output columns stay split until the item's epilogue.
 //                Per KV tile the scores of the row (half) are read from TMEM ONCE
 //                (tcgen05.ld, one wait) and the S buffer is released immediately so the next tile's QK^T overlaps
 //                this tile's softmax.  The running max is "lazy": O (in TMEM) and the row sum are rescaled only when a
@@ -30,7 +27,7 @@
 //   * MUFU.EX2 (16 / clk / SM) is the scarcest pipe: a compile-time share of the exponentials (kPolyOf8 pairs out of
 //     8) is evaluated on the FMA pipe instead -- Cody-Waite split, cubic minimax 2^f on [-0.5, 0.5] (7.5e-5 relative,
 //     1/26 of a bf16 half-ulp of P), exponent spliced in with an integer add;
-//   * setmaxnreg moves registers from warpgroup 0 to the softmax warpgroups (NS = 1: 208 each, NS = 2: 96 each;
+//   * setmaxnreg moves registers from warpgroup 0 to the softmax warpgroup(s) (NS = 1: 208 each, NS = 2: 96 each;
 //     warpgroup 0 keeps 48 -- with fewer the MMA issuer spills its descriptors and every tcgen05.mma issue costs hundreds
 //     of cycles) so the scores of a row (half) stay in registers without spills while two CTAs still share an SM;
 //   * the producer / MMA warps back off with nanosleep while blocked so their polling does not steal issue slots.
