@@ -134,6 +134,8 @@ int ca_groupnorm_apply(const void* x0, int32_t c0, const void* x1, int32_t c1, i
  *   s = x + add_rowvec[row / rows_per_vec]   (written to y_sum when non-NULL) ; y = LN(s) * gamma + beta
  * Replaces F.layer_norm in diffusers BasicTransformerBlock / TemporalBasicTransformerBlock (norm1/2/3, norm_in)
  * and the `hidden_states + emb` add at model/adapter_spatial_temporal.py:279.
+ * Constraints: c a multiple of 8, 8 <= c <= 2048; x contiguous [rows, c] and 16-byte aligned (whole rows travel as
+ * 1-D bulk copies); rows < 2^31.  y / y_sum may alias x (each row is read before it is written).
  */
 int ca_layernorm(const void* x, int64_t rows, int32_t c, float eps, const float* gamma, const float* beta,
                  const void* add_rowvec, int64_t rows_per_vec, void* y_sum, void* y, void* cuda_stream);
